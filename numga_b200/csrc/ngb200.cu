@@ -1,0 +1,1060 @@
+// numga_b200 native library: straight-line multivector programs -> sm_100a kernels.
+//
+//   IR (include/numga_b200.h)  --codegen-->  CUDA C++  --NVRTC (sm_100a, -lineinfo)-->  cubin
+//   cubin cached on disk (in-tree _kcache/, filled at build time so the GPU box does not JIT)
+//   cubin --cuModuleLoadData--> CUfunction --cuLaunchKernel--> caller's stream
+//
+// Data layout: structure-of-arrays. Component c of batch item i of an operand lives at
+// ptr[c*comp_stride + i*batch_stride]. The vectorised kernel handles batch_stride == 1 with
+// 128-bit loads/stores (4 x f32 or 2 x f64 items per thread per component row); every warp
+// therefore touches 512 contiguous bytes per component row: fully coalesced, no shared memory
+// staging needed because no data is reused between threads. Broadcast operands (batch_stride 0)
+// and everything computed only from them are evaluated once per thread before the grid-stride
+// loop (this is the "motor -> 4x4 matrix" pre-contraction of numga's sandwich_map, done in
+// registers). The kernels are persistent: grid = SMs x resident CTAs, grid-stride over the batch.
+//
+// The CUDA driver is dlopen()ed lazily, so this library loads (and compiles kernels) on a
+// machine without a GPU; launching there fails loudly with NGB200_ERR_CUDA. No CPU fallback.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/numga_b200.h"
+
+#define NGB_VERSION "0.1.0"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+extern "C" const char *ngb200_last_error(void) { return g_err.c_str(); }
+
+static std::atomic<int64_t> g_launches{0};
+extern "C" int64_t ngb200_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// CUDA driver API, resolved at first use
+// ------------------------------------------------------------------------------------------
+#define NGB_STR2(x) #x
+#define NGB_STR(x) NGB_STR2(x)
+#define DRV_FUNCS(X)                                                                              \
+    X(cuInit) X(cuGetErrorString) X(cuCtxGetCurrent) X(cuCtxSetCurrent) X(cuCtxGetDevice)         \
+    X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData)        \
+    X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute)                                \
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemAlloc) X(cuMemFree)                     \
+    X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemcpy2DAsync) X(cuStreamCreate)                \
+    X(cuStreamSynchronize) X(cuStreamDestroy) X(cuMemAllocHost) X(cuMemFreeHost)
+
+struct Driver {
+#define X(n) decltype(&n) p_##n = nullptr;
+    DRV_FUNCS(X)
+#undef X
+    bool ok = false;
+    std::string why;
+};
+static Driver g_drv;
+static std::once_flag g_drv_once;
+
+static void load_driver() {
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        g_drv.why = "CUDA driver (libcuda.so.1) not found: no GPU on this machine; numga_b200 has no CPU fallback";
+        return;
+    }
+#define X(n)                                                                                      \
+    g_drv.p_##n = (decltype(&n))dlsym(h, NGB_STR(n));                                             \
+    if (!g_drv.p_##n) { g_drv.why = std::string("missing driver symbol ") + NGB_STR(n); return; }
+    DRV_FUNCS(X)
+#undef X
+    CUresult r = g_drv.p_cuInit(0);
+    if (r != CUDA_SUCCESS) {
+        g_drv.why = "cuInit failed (" + std::to_string((int)r) + "): no usable CUDA device; numga_b200 has no CPU fallback";
+        return;
+    }
+    g_drv.ok = true;
+}
+
+static int need_driver() {
+    std::call_once(g_drv_once, load_driver);
+    if (!g_drv.ok) return fail(NGB200_ERR_CUDA, "%s", g_drv.why.c_str());
+    return NGB200_OK;
+}
+
+static int cu_fail(CUresult r, const char *what) {
+    const char *s = nullptr;
+    if (g_drv.p_cuGetErrorString) g_drv.p_cuGetErrorString(r, &s);
+    return fail(NGB200_ERR_CUDA, "%s failed: %s (%d)", what, s ? s : "?", (int)r);
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        CUresult r_ = g_drv.p_##call;                                                             \
+        if (r_ != CUDA_SUCCESS) return cu_fail(r_, #call);                                        \
+    } while (0)
+
+// make sure a context is current on this thread; returns its device ordinal
+static int current_device(int *dev_out, int want_device /* -1 = whatever is current */) {
+    CUcontext ctx = nullptr;
+    CU(cuCtxGetCurrent(&ctx));
+    if (ctx && want_device < 0) {
+        CUdevice d;
+        CU(cuCtxGetDevice(&d));
+        *dev_out = (int)d;
+        return NGB200_OK;
+    }
+    if (ctx) {
+        CUdevice d;
+        CU(cuCtxGetDevice(&d));
+        if ((int)d == want_device) { *dev_out = want_device; return NGB200_OK; }
+    }
+    CUdevice d;
+    CU(cuDeviceGet(&d, want_device < 0 ? 0 : want_device));
+    CU(cuDevicePrimaryCtxRetain(&ctx, d));
+    CU(cuCtxSetCurrent(ctx));
+    *dev_out = (int)d;
+    return NGB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// program object
+// ------------------------------------------------------------------------------------------
+static const int kMaxDevices = 32;
+
+struct Loaded {
+    std::atomic<int> ready{0};
+    CUmodule mod = nullptr;
+    CUfunction fvec = nullptr, fscalar = nullptr;
+    int regs_vec = 0, regs_scalar = 0;
+    int grid_vec = 0, grid_scalar = 0;  // persistent grid sizes (SMs x resident CTAs)
+};
+
+struct ngb200_program {
+    int dtype = 0;
+    uint32_t flags = 0;
+    std::vector<int32_t> in_width, in_mode, out_width, out_mode;
+    int n_params = 0;
+    std::vector<double> consts;
+    std::vector<ngb200_instr> instr;
+    std::vector<ngb200_store> stores;
+    int vec = 1;          // items per thread in the vector kernel (1 = no vector kernel)
+    int tpb = 256;
+    int n_live = 0, n_uniform = 0;
+    bool cache_hit = false;
+    std::string source, hash;
+    std::vector<char> cubin;
+    std::mutex mu;
+    Loaded loaded[kMaxDevices];
+    size_t param_bytes = 0;
+    bool any_indexed = false;
+};
+
+static int esize(int dtype) { return dtype == NGB200_F64 ? 8 : 4; }
+
+// ------------------------------------------------------------------------------------------
+// code generation
+// ------------------------------------------------------------------------------------------
+static void appendf(std::string &s, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n < (int)sizeof buf) { s.append(buf, n); return; }
+    std::vector<char> big(n + 1);
+    va_start(ap, fmt);
+    vsnprintf(big.data(), big.size(), fmt, ap);
+    va_end(ap);
+    s.append(big.data(), n);
+}
+
+static std::string literal(double v, int dtype) {
+    char buf[64];
+    if (dtype == NGB200_F32) {
+        float f = (float)v;
+        if (std::isnan(f)) return "__int_as_float(0x7fc00000)";
+        if (std::isinf(f)) return f > 0 ? "__int_as_float(0x7f800000)" : "__int_as_float(0xff800000)";
+        snprintf(buf, sizeof buf, "%af", (double)f);
+    } else {
+        if (std::isnan(v)) return "__longlong_as_double(0x7ff8000000000000LL)";
+        if (std::isinf(v)) return v > 0 ? "__longlong_as_double(0x7ff0000000000000LL)" : "__longlong_as_double(0xfff0000000000000LL)";
+        snprintf(buf, sizeof buf, "%a", v);
+    }
+    std::string s(buf);
+    if (s[0] == '-') s = "(" + s + ")";
+    return s;
+}
+
+static int n_operands_of(int op) {
+    switch (op) {
+        case NGB200_OP_INPUT: case NGB200_OP_CONST: case NGB200_OP_PARAM: return 0;
+        case NGB200_OP_NEG: case NGB200_OP_SQRT: case NGB200_OP_RSQRT: case NGB200_OP_RCP: case NGB200_OP_ABS:
+        case NGB200_OP_EXP: case NGB200_OP_LOG: case NGB200_OP_SIN: case NGB200_OP_COS: return 1;
+        case NGB200_OP_FMA: case NGB200_OP_SELECT_GT0: return 3;
+        default: return 2;
+    }
+}
+
+struct Gen {
+    const ngb200_program &P;
+    bool f64, faithful;
+    std::vector<char> live, uniform;
+    std::vector<int> uslot;   // export slot of uniform values used by varying code
+    std::vector<int> xoff;    // offset of each varying input in x[]
+    std::vector<int> yoff;    // offset of each output in y[]
+    int NX = 0, NU = 0, NY = 0;
+
+    explicit Gen(const ngb200_program &p)
+        : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {}
+
+    // name of value v as seen from uniform (preamble) or varying (body) code
+    std::string ref(int v, bool in_body) const {
+        const ngb200_instr &I = P.instr[v];
+        if (I.op == NGB200_OP_CONST) return literal(P.consts[I.a], P.dtype);
+        if (in_body) {
+            if (uniform[v]) return "u[" + std::to_string(uslot[v]) + "]";
+            if (I.op == NGB200_OP_INPUT) return "x[" + std::to_string(xoff[I.a] + I.b) + "]";
+            return "r" + std::to_string(v);
+        }
+        return "q" + std::to_string(v);
+    }
+
+    std::string expr(int v, bool in_body) const {
+        const ngb200_instr &I = P.instr[v];
+        std::string a = n_operands_of(I.op) >= 1 ? ref(I.a, in_body) : "";
+        std::string b = n_operands_of(I.op) >= 2 ? ref(I.b, in_body) : "";
+        std::string c = n_operands_of(I.op) >= 3 ? ref(I.c, in_body) : "";
+        const char *sfx = f64 ? "" : "f";
+        auto rn = [&](const char *op) { return std::string(f64 ? "__d" : "__f") + op + "_rn"; };
+        switch (I.op) {
+            case NGB200_OP_ADD: return faithful ? rn("add") + "(" + a + ", " + b + ")" : a + " + " + b;
+            case NGB200_OP_SUB: return faithful ? rn("sub") + "(" + a + ", " + b + ")" : a + " - " + b;
+            case NGB200_OP_MUL: return faithful ? rn("mul") + "(" + a + ", " + b + ")" : a + " * " + b;
+            case NGB200_OP_DIV: return faithful ? rn("div") + "(" + a + ", " + b + ")" : a + " / " + b;
+            case NGB200_OP_NEG: return "-" + a;
+            case NGB200_OP_SQRT: return faithful ? rn("sqrt") + "(" + a + ")" : std::string("sqrt") + sfx + "(" + a + ")";
+            case NGB200_OP_RSQRT:
+                return faithful ? rn("div") + "(T(1), " + rn("sqrt") + "(" + a + "))"
+                                : std::string("T(1) / sqrt") + sfx + "(" + a + ")";
+            case NGB200_OP_RCP: return faithful ? rn("div") + "(T(1), " + a + ")" : "T(1) / " + a;
+            case NGB200_OP_ABS: return std::string("fabs") + sfx + "(" + a + ")";
+            case NGB200_OP_NAN_TO_NUM: return "ngb_nan_to_num(" + a + ", " + b + ")";
+            case NGB200_OP_FMA: return std::string("fma") + sfx + "(" + a + ", " + b + ", " + c + ")";
+            case NGB200_OP_EXP: return std::string("exp") + sfx + "(" + a + ")";
+            case NGB200_OP_LOG: return std::string("log") + sfx + "(" + a + ")";
+            case NGB200_OP_SIN: return std::string("sin") + sfx + "(" + a + ")";
+            case NGB200_OP_COS: return std::string("cos") + sfx + "(" + a + ")";
+            case NGB200_OP_MIN: return std::string("fmin") + sfx + "(" + a + ", " + b + ")";
+            case NGB200_OP_MAX: return std::string("fmax") + sfx + "(" + a + ", " + b + ")";
+            case NGB200_OP_SELECT_GT0: return "(" + a + " > T(0) ? " + b + " : " + c + ")";
+        }
+        return "T(0)";
+    }
+
+    int analyse() {
+        const int n = (int)P.instr.size();
+        live.assign(n, 0);
+        uniform.assign(n, 0);
+        uslot.assign(n, -1);
+        // validate + uniformity (forward)
+        for (int v = 0; v < n; ++v) {
+            const ngb200_instr &I = P.instr[v];
+            if (I.op < 0 || I.op >= NGB200_OP_COUNT_) return fail(NGB200_ERR_INVALID, "instr %d: bad opcode %d", v, I.op);
+            int k = n_operands_of(I.op);
+            const int ops[3] = {I.a, I.b, I.c};
+            for (int j = 0; j < k; ++j)
+                if (ops[j] < 0 || ops[j] >= v) return fail(NGB200_ERR_INVALID, "instr %d: operand %d out of range", v, ops[j]);
+            if (I.op == NGB200_OP_INPUT) {
+                if (I.a < 0 || I.a >= (int)P.in_width.size() || I.b < 0 || I.b >= P.in_width[I.a])
+                    return fail(NGB200_ERR_INVALID, "instr %d: input (%d,%d) out of range", v, I.a, I.b);
+                uniform[v] = P.in_mode[I.a] == NGB200_BROADCAST;
+            } else if (I.op == NGB200_OP_CONST) {
+                if (I.a < 0 || I.a >= (int)P.consts.size()) return fail(NGB200_ERR_INVALID, "instr %d: const out of range", v);
+                uniform[v] = 1;
+            } else if (I.op == NGB200_OP_PARAM) {
+                if (I.a < 0 || I.a >= P.n_params) return fail(NGB200_ERR_INVALID, "instr %d: param out of range", v);
+                uniform[v] = 1;
+            } else {
+                bool u = true;
+                for (int j = 0; j < k; ++j) u = u && uniform[ops[j]];
+                uniform[v] = u;
+            }
+        }
+        // liveness (backward from the stores)
+        for (const ngb200_store &s : P.stores) {
+            if (s.operand < 0 || s.operand >= (int)P.out_width.size() || s.component < 0 ||
+                s.component >= P.out_width[s.operand] || s.value < 0 || s.value >= n)
+                return fail(NGB200_ERR_INVALID, "store (%d,%d,%d) out of range", s.operand, s.component, s.value);
+            live[s.value] = 1;
+        }
+        for (int v = n - 1; v >= 0; --v) {
+            if (!live[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            int k = n_operands_of(I.op);
+            const int ops[3] = {I.a, I.b, I.c};
+            for (int j = 0; j < k; ++j) live[ops[j]] = 1;
+        }
+        // uniform values referenced from varying code or stored need an export slot
+        auto want_slot = [&](int v) {
+            if (uniform[v] && P.instr[v].op != NGB200_OP_CONST && uslot[v] < 0) uslot[v] = NU++;
+        };
+        for (int v = 0; v < n; ++v) {
+            if (!live[v] || uniform[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            int k = n_operands_of(I.op);
+            const int ops[3] = {I.a, I.b, I.c};
+            for (int j = 0; j < k; ++j) want_slot(ops[j]);
+        }
+        for (const ngb200_store &s : P.stores) want_slot(s.value);
+        xoff.assign(P.in_width.size(), 0);
+        for (size_t k = 0; k < P.in_width.size(); ++k) {
+            xoff[k] = NX;
+            if (P.in_mode[k] != NGB200_BROADCAST) NX += P.in_width[k];
+        }
+        yoff.assign(P.out_width.size(), 0);
+        for (size_t k = 0; k < P.out_width.size(); ++k) { yoff[k] = NY; NY += P.out_width[k]; }
+        return NGB200_OK;
+    }
+
+    std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform) {
+        const int n = (int)P.instr.size();
+        const int nin = (int)P.in_width.size(), nout = (int)P.out_width.size();
+        const char *T = f64 ? "double" : "float";
+        const char *VT = f64 ? "double2" : (vec == 2 ? "float2" : "float4");
+        static const char *lane[4] = {"x", "y", "z", "w"};
+        std::string s;
+        appendf(s, "// numga_b200 generated kernel (dtype %s, %s, vec %d)\n", T, faithful ? "faithful" : "fast", vec);
+        appendf(s, "typedef %s T;\ntypedef %s VT;\n", T, VT);
+        appendf(s, "#define NGB_V %d\n#define NGB_TPB %d\n", vec, P.tpb);
+        s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
+        appendf(s, "struct Params { Operand in[%d]; Operand out[%d]; double scal[%d]; long long n; };\n",
+                nin > 0 ? nin : 1, nout > 0 ? nout : 1, P.n_params > 0 ? P.n_params : 1);
+        if (f64)
+            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysign(1.7976931348623157e308, a) : a); }\n";
+        else
+            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysignf(3.4028234663852886e38f, a) : a); }\n";
+        const char *ld = ldmode == 0 ? "*" : ldmode == 1 ? "__ldg" : ldmode == 2 ? "__ldcs" : "__ldlu";
+        appendf(s, "#define NGB_LD(p) %s(p)\n", ld);
+        if (stmode == 0) s += "#define NGB_ST(p, v) (*(p) = (v))\n";
+        else appendf(s, "#define NGB_ST(p, v) %s((p), (v))\n", stmode == 1 ? "__stcs" : stmode == 2 ? "__stcg" : "__stwt");
+
+        // ---- uniform preamble -------------------------------------------------------------
+        int nl = 0, nu = 0;
+        appendf(s, "__device__ __forceinline__ void ngb_uniform(const Params& p, T (&u)[%d]) {\n", NU > 0 ? NU : 1);
+        for (int v = 0; v < n; ++v) {
+            if (!live[v] || !uniform[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            if (I.op == NGB200_OP_CONST) continue;
+            ++nl; ++nu;
+            if (I.op == NGB200_OP_INPUT)
+                appendf(s, "  const T q%d = __ldg(p.in[%d].ptr + %dLL * p.in[%d].cs);\n", v, I.a, I.b, I.a);
+            else if (I.op == NGB200_OP_PARAM)
+                appendf(s, "  const T q%d = (T)p.scal[%d];\n", v, I.a);
+            else
+                appendf(s, "  const T q%d = %s;\n", v, expr(v, false).c_str());
+            if (uslot[v] >= 0) appendf(s, "  u[%d] = q%d;\n", uslot[v], v);
+        }
+        s += "}\n";
+
+        // ---- per-item body ----------------------------------------------------------------
+        appendf(s, "__device__ __forceinline__ void ngb_body(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
+                NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
+        for (int v = 0; v < n; ++v) {
+            if (!live[v] || uniform[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            if (I.op == NGB200_OP_INPUT) continue;
+            ++nl;
+            appendf(s, "  const T r%d = %s;\n", v, expr(v, true).c_str());
+        }
+        std::vector<int> stored(NY > 0 ? NY : 1, -1);
+        for (const ngb200_store &st : P.stores) stored[yoff[st.operand] + st.component] = st.value;
+        for (int j = 0; j < NY; ++j) {
+            if (stored[j] >= 0) appendf(s, "  y[%d] = %s;\n", j, ref(stored[j], true).c_str());
+            else appendf(s, "  y[%d] = T(0);\n", j);
+        }
+        s += "}\n";
+        *n_live = nl;
+        *n_uniform = nu;
+
+        // ---- scalar kernel: any strides, gather/scatter -----------------------------------
+        appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_scalar(const Params p) {\n");
+        appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+        s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
+        s += "  for (long long i = (long long)blockIdx.x * NGB_TPB + threadIdx.x; i < p.n; i += stride) {\n";
+        appendf(s, "    T x[%d]; T y[%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
+        for (int k = 0; k < nin; ++k) {
+            if (P.in_mode[k] == NGB200_BROADCAST) continue;
+            if (P.in_mode[k] == NGB200_INDEXED)
+                appendf(s, "    const T* in%d = p.in[%d].ptr + p.in[%d].index[i] * p.in[%d].bs;\n", k, k, k, k);
+            else
+                appendf(s, "    const T* in%d = p.in[%d].ptr + i * p.in[%d].bs;\n", k, k, k);
+            for (int c = 0; c < P.in_width[k]; ++c)
+                appendf(s, "    x[%d] = NGB_LD(in%d + %dLL * p.in[%d].cs);\n", xoff[k] + c, k, c, k);
+        }
+        s += "    ngb_body(x, u, y);\n";
+        for (int k = 0; k < nout; ++k) {
+            if (P.out_mode[k] == NGB200_INDEXED)
+                appendf(s, "    T* out%d = p.out[%d].ptr + p.out[%d].index[i] * p.out[%d].bs;\n", k, k, k, k);
+            else
+                appendf(s, "    T* out%d = p.out[%d].ptr + i * p.out[%d].bs;\n", k, k, k);
+            for (int c = 0; c < P.out_width[k]; ++c)
+                appendf(s, "    NGB_ST(out%d + %dLL * p.out[%d].cs, y[%d]);\n", k, c, k, yoff[k] + c);
+        }
+        s += "  }\n}\n";
+
+        // ---- vector kernel: batch_stride 1, 128-bit accesses --------------------------------
+        if (vec > 1) {
+            appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_vec(const Params p) {\n");
+            appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+            s += "  const long long nvec = p.n / NGB_V;\n";
+            s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
+            s += "  for (long long v = (long long)blockIdx.x * NGB_TPB + threadIdx.x; v < nvec; v += stride) {\n";
+            appendf(s, "    T x[NGB_V][%d]; T y[NGB_V][%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
+            for (int k = 0; k < nin; ++k) {
+                if (P.in_mode[k] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < P.in_width[k]; ++c) {
+                    appendf(s, "    { const VT t = NGB_LD(reinterpret_cast<const VT*>(p.in[%d].ptr + %dLL * p.in[%d].cs) + v);", k, c, k);
+                    for (int l = 0; l < vec; ++l) appendf(s, " x[%d][%d] = t.%s;", l, xoff[k] + c, lane[l]);
+                    s += " }\n";
+                }
+            }
+            s += "    #pragma unroll\n    for (int l = 0; l < NGB_V; ++l) ngb_body(x[l], u, y[l]);\n";
+            for (int k = 0; k < nout; ++k)
+                for (int c = 0; c < P.out_width[k]; ++c) {
+                    s += "    { VT t;";
+                    for (int l = 0; l < vec; ++l) appendf(s, " t.%s = y[%d][%d];", lane[l], l, yoff[k] + c);
+                    appendf(s, " NGB_ST(reinterpret_cast<VT*>(p.out[%d].ptr + %dLL * p.out[%d].cs) + v, t); }\n", k, c, k);
+                }
+            s += "  }\n}\n";
+        }
+        return s;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// cache + NVRTC
+// ------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::string g_cache_dir;
+
+static std::string default_cache_dir() {
+    const char *env = getenv("NGB200_CACHE_DIR");
+    if (env && *env) return env;
+    Dl_info info;
+    if (dladdr((void *)&ngb200_last_error, &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        size_t k = p.rfind('/');
+        if (k != std::string::npos) return p.substr(0, k) + "/_kcache";
+    }
+    return "/tmp/numga_b200_kcache";
+}
+
+extern "C" int ngb200_set_cache_dir(const char *path) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cache_dir = path ? path : "";
+    return NGB200_OK;
+}
+
+static std::string cache_dir() {
+    if (g_cache_dir.empty()) g_cache_dir = default_cache_dir();
+    mkdir(g_cache_dir.c_str(), 0755);
+    return g_cache_dir;
+}
+
+static std::string hash_hex(const std::string &s) {
+    uint64_t a = 1469598103934665603ULL, b = 0x9E3779B97F4A7C15ULL;
+    for (unsigned char ch : s) {
+        a = (a ^ ch) * 1099511628211ULL;
+        b = (b + ch) * 0xD6E8FEB86659FD93ULL;
+        b ^= b >> 32;
+    }
+    char buf[40];
+    snprintf(buf, sizeof buf, "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+    return buf;
+}
+
+static bool read_file(const std::string &path, std::vector<char> &out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? n : 0);
+    bool ok = n > 0 && fread(out.data(), 1, n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+static void write_file(const std::string &path, const char *data, size_t n) {
+    std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    fwrite(data, 1, n, f);
+    fclose(f);
+    rename(tmp.c_str(), path.c_str());
+}
+
+static int nvrtc_compile(const std::string &src, std::vector<char> &cubin) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "ngb200_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(NGB200_ERR_COMPILE, "nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--fmad=true",
+                          "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
+    nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof opts / sizeof *opts), opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, 0);
+        nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        return fail(NGB200_ERR_COMPILE, "NVRTC: %s\n%.3000s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t n = 0;
+    nvrtcGetCUBINSize(prog, &n);
+    cubin.resize(n);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    if (n == 0) return fail(NGB200_ERR_COMPILE, "NVRTC produced no cubin");
+    return NGB200_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+static int finish_program(ngb200_program *P, int vec_hint) {
+    for (int m : P->in_mode) P->any_indexed |= (m == NGB200_INDEXED);
+    for (int m : P->out_mode) P->any_indexed |= (m == NGB200_INDEXED);
+    Gen gen(*P);
+    int rc = gen.analyse();
+    if (rc) return rc;
+    int live_guess = 0;
+    for (char c : gen.live) live_guess += c;
+    int vmax = P->dtype == NGB200_F64 ? 2 : 4;
+    int vec = vec_hint > 0 ? vec_hint : (live_guess <= env_int("NGB200_VEC_INSTR_LIMIT", 700) ? vmax : 1);
+    if (vec > vmax) vec = vmax;
+    if (vec == 3) vec = 2;
+    if (P->any_indexed || gen.NX == 0) vec = 1;
+    P->vec = vec;
+    P->tpb = env_int("NGB200_TPB", 256);
+    P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform);
+    P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
+                     8 * (P->n_params > 0 ? P->n_params : 1) + 8;
+    if (P->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel (%zu parameter bytes)", P->param_bytes);
+
+    // the key is the generated source alone: a cubin built at build() time by this image's NVRTC stays
+    // valid when torch's bundled (older) libnvrtc happens to be the one loaded in the process
+    P->hash = hash_hex(P->source + "|sm_100a");
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::string base = cache_dir() + "/" + P->hash;
+    if (!env_int("NGB200_NO_CACHE", 0) && read_file(base + ".cubin", P->cubin)) {
+        P->cache_hit = true;
+        return NGB200_OK;
+    }
+    rc = nvrtc_compile(P->source, P->cubin);
+    if (rc) return rc;
+    write_file(base + ".cubin", P->cubin.data(), P->cubin.size());
+    write_file(base + ".cu", P->source.data(), P->source.size());
+    return NGB200_OK;
+}
+
+extern "C" int ngb200_program_create(const ngb200_program_desc *d, ngb200_program **out) {
+    if (!d || !out) return fail(NGB200_ERR_INVALID, "null argument");
+    if (d->dtype != NGB200_F32 && d->dtype != NGB200_F64) return fail(NGB200_ERR_INVALID, "bad dtype %d", d->dtype);
+    if (d->n_inputs < 0 || d->n_outputs < 1 || d->n_instr < 0 || d->n_stores < 0 || d->n_consts < 0 || d->n_params < 0)
+        return fail(NGB200_ERR_INVALID, "bad counts in program description");
+    ngb200_program *P = new ngb200_program;
+    P->dtype = d->dtype;
+    P->flags = d->flags;
+    P->in_width.assign(d->input_width, d->input_width + d->n_inputs);
+    if (d->input_mode) P->in_mode.assign(d->input_mode, d->input_mode + d->n_inputs);
+    else P->in_mode.assign(d->n_inputs, NGB200_VARYING);
+    P->out_width.assign(d->output_width, d->output_width + d->n_outputs);
+    if (d->output_mode) P->out_mode.assign(d->output_mode, d->output_mode + d->n_outputs);
+    else P->out_mode.assign(d->n_outputs, NGB200_VARYING);
+    P->n_params = d->n_params;
+    if (d->n_consts) P->consts.assign(d->consts, d->consts + d->n_consts);
+    if (d->n_instr) P->instr.assign(d->instr, d->instr + d->n_instr);
+    if (d->n_stores) P->stores.assign(d->stores, d->stores + d->n_stores);
+    for (int w : P->in_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad input width"); }
+    for (int w : P->out_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad output width"); }
+    for (int m : P->in_mode) if (m < 0 || m > 2) { delete P; return fail(NGB200_ERR_INVALID, "bad input mode"); }
+    for (int m : P->out_mode) if (m != NGB200_VARYING && m != NGB200_INDEXED) { delete P; return fail(NGB200_ERR_INVALID, "bad output mode"); }
+    int rc = finish_program(P, d->vec);
+    if (rc) { delete P; return rc; }
+    *out = P;
+    return NGB200_OK;
+}
+
+// ---- operator from its term table -----------------------------------------------------------
+struct Builder {
+    std::vector<ngb200_instr> code;
+    std::vector<double> consts;
+    std::map<std::vector<int32_t>, int> memo;
+    int emit(int op, int a = 0, int b = 0, int c = 0) {
+        if ((op == NGB200_OP_ADD || op == NGB200_OP_MUL) && a > b) std::swap(a, b);  // exact: IEEE add/mul commute
+        std::vector<int32_t> key = {op, a, b, c};
+        auto it = memo.find(key);
+        if (it != memo.end()) return it->second;
+        code.push_back({op, a, b, c});
+        return memo[key] = (int)code.size() - 1;
+    }
+    int constant(double v) {
+        for (size_t k = 0; k < consts.size(); ++k)
+            if (consts[k] == v) return emit(NGB200_OP_CONST, (int)k);
+        consts.push_back(v);
+        return emit(NGB200_OP_CONST, (int)consts.size() - 1);
+    }
+};
+
+extern "C" int ngb200_operator_create(const int32_t *terms, int32_t n_terms, int32_t arity, const int32_t *n_in,
+                                      int32_t n_out, int32_t dtype, uint32_t bcast_mask, uint32_t flags,
+                                      ngb200_program **out) {
+    if (!out || arity < 1 || arity > 8 || n_terms < 0 || (n_terms && !terms) || !n_in || n_out < 1)
+        return fail(NGB200_ERR_INVALID, "bad operator description");
+    const bool faithful = flags & NGB200_FAITHFUL;
+    const int w = arity + 2;
+    for (int t = 0; t < n_terms; ++t) {
+        for (int k = 0; k < arity; ++k)
+            if (terms[t * w + k] < 0 || terms[t * w + k] >= n_in[k]) return fail(NGB200_ERR_INVALID, "term %d: input index out of range", t);
+        if (terms[t * w + arity] < 0 || terms[t * w + arity] >= n_out) return fail(NGB200_ERR_INVALID, "term %d: output index out of range", t);
+    }
+    Builder B;
+    std::vector<int32_t> in_mode(arity);
+    bool any_b = false, any_v = false;
+    for (int k = 0; k < arity; ++k) {
+        in_mode[k] = (bcast_mask >> k) & 1 ? NGB200_BROADCAST : NGB200_VARYING;
+        (in_mode[k] == NGB200_BROADCAST ? any_b : any_v) = true;
+    }
+    auto input = [&](int k, int i) { return B.emit(NGB200_OP_INPUT, k, i); };
+    auto signed_product = [&](const int32_t *term, bool want_bcast, bool want_varying, int coeff) -> int {
+        // product of the selected factors, right-associated a0*(a1*(a2..)) -- the order in which
+        // numpy's einsum contracts, so FAITHFUL ternary operators are bit-exact too; coefficient last
+        int acc = -1;
+        for (int k = arity - 1; k >= 0; --k) {
+            bool bc = in_mode[k] == NGB200_BROADCAST;
+            if ((bc && !want_bcast) || (!bc && !want_varying)) continue;
+            int x = input(k, term[k]);
+            acc = acc < 0 ? x : B.emit(NGB200_OP_MUL, acc, x);
+        }
+        if (acc < 0) acc = B.constant(1.0);
+        if (coeff == -1) acc = B.emit(NGB200_OP_NEG, acc);
+        else if (coeff != 1) acc = B.emit(NGB200_OP_MUL, acc, B.constant((double)coeff));
+        return acc;
+    };
+    std::vector<ngb200_store> stores;
+    for (int o = 0; o < n_out; ++o) {
+        int acc = -1;
+        if (!faithful && any_b && any_v) {
+            // pre-contract the broadcast operands: out[o] = sum_J (sum c * prod bcast) * prod varying[J]
+            std::vector<std::vector<int32_t>> keys;
+            std::vector<int> ucoef;
+            for (int t = 0; t < n_terms; ++t) {
+                const int32_t *term = terms + t * w;
+                if (term[arity] != o) continue;
+                std::vector<int32_t> key;
+                for (int k = 0; k < arity; ++k) if (in_mode[k] != NGB200_BROADCAST) key.push_back(term[k]);
+                int up = signed_product(term, true, false, term[arity + 1]);
+                size_t j = 0;
+                for (; j < keys.size(); ++j) if (keys[j] == key) break;
+                if (j == keys.size()) { keys.push_back(key); ucoef.push_back(up); }
+                else ucoef[j] = B.emit(NGB200_OP_ADD, ucoef[j], up);
+            }
+            for (size_t j = 0; j < keys.size(); ++j) {
+                int vp = -1, kk = 0;
+                for (int k = 0; k < arity; ++k) {
+                    if (in_mode[k] == NGB200_BROADCAST) continue;
+                    int x = input(k, keys[j][kk++]);
+                    vp = vp < 0 ? x : B.emit(NGB200_OP_MUL, vp, x);
+                }
+                int prod = B.emit(NGB200_OP_MUL, ucoef[j], vp);
+                acc = acc < 0 ? prod : B.emit(NGB200_OP_ADD, acc, prod);
+            }
+        } else {
+            for (int t = 0; t < n_terms; ++t) {
+                const int32_t *term = terms + t * w;
+                if (term[arity] != o) continue;
+                int c = term[arity + 1];
+                int prod = signed_product(term, true, true, c == -1 ? 1 : c);
+                if (acc < 0) acc = c == -1 ? B.emit(NGB200_OP_NEG, prod) : prod;
+                else acc = B.emit(c == -1 ? NGB200_OP_SUB : NGB200_OP_ADD, acc, prod);  // a - p == a + (-p) exactly
+            }
+        }
+        if (acc >= 0) stores.push_back({0, o, acc});
+    }
+    ngb200_program_desc d;
+    memset(&d, 0, sizeof d);
+    d.dtype = dtype;
+    d.flags = flags;
+    d.n_inputs = arity;
+    d.input_width = n_in;
+    d.input_mode = in_mode.data();
+    d.n_outputs = 1;
+    d.output_width = &n_out;
+    d.n_consts = (int)B.consts.size();
+    d.consts = B.consts.data();
+    d.n_instr = (int)B.code.size();
+    d.instr = B.code.data();
+    d.n_stores = (int)stores.size();
+    d.stores = stores.data();
+    return ngb200_program_create(&d, out);
+}
+
+extern "C" void ngb200_program_destroy(ngb200_program *P) { delete P; }
+
+extern "C" const char *ngb200_program_source(const ngb200_program *P) { return P ? P->source.c_str() : ""; }
+
+extern "C" int ngb200_program_get_info(const ngb200_program *P, ngb200_program_info *info) {
+    if (!P || !info) return fail(NGB200_ERR_INVALID, "null argument");
+    memset(info, 0, sizeof *info);
+    info->n_instr = P->n_live;
+    info->n_uniform = P->n_uniform;
+    info->vec = P->vec;
+    info->cache_hit = P->cache_hit;
+    info->cubin_bytes = (int64_t)P->cubin.size();
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (P->loaded[d].ready.load()) { info->regs_vec = P->loaded[d].regs_vec; info->regs_scalar = P->loaded[d].regs_scalar; break; }
+    return NGB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// loading + launching
+// ------------------------------------------------------------------------------------------
+static int load_on_device(ngb200_program *P, int dev, Loaded **out) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(NGB200_ERR_CUDA, "device ordinal %d not supported", dev);
+    Loaded &L = P->loaded[dev];
+    if (!L.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(P->mu);
+        if (!L.ready.load()) {
+            CU(cuModuleLoadData(&L.mod, P->cubin.data()));
+            CU(cuModuleGetFunction(&L.fscalar, L.mod, "ngb_scalar"));
+            int sms = 0;
+            CU(cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+            int waves = env_int("NGB200_WAVES", 8), nb = 0;
+            CU(cuFuncGetAttribute(&L.regs_scalar, CU_FUNC_ATTRIBUTE_NUM_REGS, L.fscalar));
+            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fscalar, P->tpb, 0));
+            L.grid_scalar = sms * (nb > 0 ? nb : 1) * waves;
+            if (P->vec > 1) {
+                CU(cuModuleGetFunction(&L.fvec, L.mod, "ngb_vec"));
+                CU(cuFuncGetAttribute(&L.regs_vec, CU_FUNC_ATTRIBUTE_NUM_REGS, L.fvec));
+                CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fvec, P->tpb, 0));
+                L.grid_vec = sms * (nb > 0 ? nb : 1) * waves;
+            }
+            L.ready.store(1, std::memory_order_release);
+        }
+    }
+    *out = &L;
+    return NGB200_OK;
+}
+
+struct DevOperand {
+    void *ptr;
+    long long cs, bs;
+    const long long *index;
+};
+
+static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t work, const ngb200_operand *in,
+                      const ngb200_operand *out, const double *params, int64_t n, int64_t offset, CUstream stream) {
+    const size_t nin = P->in_width.size(), nout = P->out_width.size();
+    const size_t nin_s = nin ? nin : 1, nout_s = nout ? nout : 1, np_s = P->n_params > 0 ? P->n_params : 1;
+    std::vector<char> buf(P->param_bytes, 0);
+    DevOperand *o = reinterpret_cast<DevOperand *>(buf.data());
+    const int es = esize(P->dtype);
+    for (size_t k = 0; k < nin; ++k) {
+        bool moves = P->in_mode[k] == NGB200_VARYING;
+        o[k] = {(char *)in[k].ptr + (moves ? offset * in[k].batch_stride * es : 0), in[k].comp_stride,
+                P->in_mode[k] == NGB200_BROADCAST ? 0 : in[k].batch_stride,
+                P->in_mode[k] == NGB200_INDEXED ? (const long long *)in[k].index + offset : nullptr};
+    }
+    for (size_t k = 0; k < nout; ++k) {
+        bool moves = P->out_mode[k] == NGB200_VARYING;
+        o[nin_s + k] = {(char *)out[k].ptr + (moves ? offset * out[k].batch_stride * es : 0), out[k].comp_stride,
+                        out[k].batch_stride,
+                        P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr};
+    }
+    double *sc = reinterpret_cast<double *>(buf.data() + 32 * (nin_s + nout_s));
+    for (int k = 0; k < P->n_params; ++k) sc[k] = params ? params[k] : 0.0;
+    *reinterpret_cast<long long *>(buf.data() + 32 * (nin_s + nout_s) + 8 * np_s) = n;
+    int64_t blocks = (work + P->tpb - 1) / P->tpb;
+    if (blocks > grid_cap) blocks = grid_cap;
+    if (blocks < 1) blocks = 1;
+    void *args[] = {buf.data()};
+    CU(cuLaunchKernel(f, (unsigned)blocks, 1, 1, (unsigned)P->tpb, 1, 1, 0, stream, args, nullptr));
+    g_launches.fetch_add(1);
+    return NGB200_OK;
+}
+
+extern "C" int ngb200_program_launch(ngb200_program *P, const ngb200_operand *in, const ngb200_operand *out,
+                                     const double *params, int64_t batch, void *stream) {
+    if (!P || (!in && !P->in_width.empty()) || !out) return fail(NGB200_ERR_INVALID, "null argument");
+    if (batch < 0) return fail(NGB200_ERR_INVALID, "negative batch");
+    if (P->n_params > 0 && !params) return fail(NGB200_ERR_INVALID, "program needs %d scalar params", P->n_params);
+    int rc = need_driver();
+    if (rc) return rc;
+    if (batch == 0) return NGB200_OK;
+    int dev = 0;
+    rc = current_device(&dev, -1);
+    if (rc) return rc;
+    Loaded *L = nullptr;
+    rc = load_on_device(P, dev, &L);
+    if (rc) return rc;
+    const int es = esize(P->dtype);
+    for (size_t k = 0; k < P->in_width.size(); ++k) {
+        if (P->in_width[k] > 0 && !in[k].ptr) return fail(NGB200_ERR_INVALID, "input %zu: null pointer", k);
+        if (P->in_mode[k] == NGB200_INDEXED && !in[k].index) return fail(NGB200_ERR_INVALID, "input %zu: indexed operand without index", k);
+    }
+    for (size_t k = 0; k < P->out_width.size(); ++k) {
+        if (P->out_width[k] > 0 && !out[k].ptr) return fail(NGB200_ERR_INVALID, "output %zu: null pointer", k);
+        if (P->out_mode[k] == NGB200_INDEXED && !out[k].index) return fail(NGB200_ERR_INVALID, "output %zu: indexed operand without index", k);
+    }
+    bool vec_ok = P->vec > 1 && batch >= P->vec;
+    if (vec_ok) {
+        auto aligned = [&](const ngb200_operand &o, int width) {
+            if (width == 0) return true;
+            return o.batch_stride == 1 && ((uintptr_t)o.ptr % 16 == 0) && (width == 1 || (o.comp_stride * es) % 16 == 0);
+        };
+        for (size_t k = 0; k < P->in_width.size() && vec_ok; ++k)
+            if (P->in_mode[k] == NGB200_VARYING) vec_ok = aligned(in[k], P->in_width[k]);
+        for (size_t k = 0; k < P->out_width.size() && vec_ok; ++k) vec_ok = aligned(out[k], P->out_width[k]);
+    }
+    CUstream s = (CUstream)stream;
+    if (vec_ok) {
+        int64_t nvec = batch / P->vec, done = nvec * P->vec;
+        rc = launch_one(P, L->fvec, L->grid_vec, nvec, in, out, params, done, 0, s);
+        if (rc) return rc;
+        if (done < batch) rc = launch_one(P, L->fscalar, L->grid_scalar, batch - done, in, out, params, batch - done, done, s);
+        return rc;
+    }
+    return launch_one(P, L->fscalar, L->grid_scalar, batch, in, out, params, batch, 0, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer execution: chunked H2D -> kernel -> D2H over several streams
+// ------------------------------------------------------------------------------------------
+extern "C" int ngb200_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(NGB200_ERR_INVALID, "bad argument");
+    int rc = need_driver();
+    if (rc) return rc;
+    int dev;
+    rc = current_device(&dev, -1);
+    if (rc) return rc;
+    CU(cuMemAllocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return NGB200_OK;
+}
+
+extern "C" int ngb200_host_free(void *ptr) {
+    int rc = need_driver();
+    if (rc) return rc;
+    CU(cuMemFreeHost(ptr));
+    return NGB200_OK;
+}
+
+namespace {
+struct Slot {
+    CUstream stream = nullptr;
+    std::vector<CUdeviceptr> in, out;
+};
+struct HostRun {
+    std::vector<Slot> slots;
+    std::vector<CUdeviceptr> bcast;
+    ~HostRun() {
+        for (Slot &s : slots) {
+            for (CUdeviceptr p : s.in) if (p) g_drv.p_cuMemFree(p);
+            for (CUdeviceptr p : s.out) if (p) g_drv.p_cuMemFree(p);
+            if (s.stream) g_drv.p_cuStreamDestroy(s.stream);
+        }
+        for (CUdeviceptr p : bcast) if (p) g_drv.p_cuMemFree(p);
+    }
+};
+}  // namespace
+
+// copy `items` batch items of one operand between host layout and a device SoA/AoS chunk buffer
+static int copy_chunk(bool to_device, const ngb200_operand &h, int width, int es, int64_t first, int64_t items,
+                      CUdeviceptr d, int64_t d_cs, CUstream s) {
+    if (width == 0 || items == 0) return NGB200_OK;
+    if (h.batch_stride == 1) {  // SoA on the host: one row per component
+        CUDA_MEMCPY2D c;
+        memset(&c, 0, sizeof c);
+        c.WidthInBytes = (size_t)items * es;
+        c.Height = (size_t)width;
+        char *hp = (char *)h.ptr + first * es;
+        if (to_device) {
+            c.srcMemoryType = CU_MEMORYTYPE_HOST; c.srcHost = hp; c.srcPitch = (size_t)h.comp_stride * es;
+            c.dstMemoryType = CU_MEMORYTYPE_DEVICE; c.dstDevice = d; c.dstPitch = (size_t)d_cs * es;
+        } else {
+            c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = hp; c.dstPitch = (size_t)h.comp_stride * es;
+            c.srcMemoryType = CU_MEMORYTYPE_DEVICE; c.srcDevice = d; c.srcPitch = (size_t)d_cs * es;
+        }
+        if (width == 1) { c.srcPitch = c.dstPitch = c.WidthInBytes; }
+        CU(cuMemcpy2DAsync(&c, s));
+        return NGB200_OK;
+    }
+    if (h.comp_stride == 1 && h.batch_stride == width) {  // AoS on the host: one contiguous block
+        char *hp = (char *)h.ptr + first * width * es;
+        if (to_device) CU(cuMemcpyHtoDAsync(d, hp, (size_t)items * width * es, s));
+        else CU(cuMemcpyDtoHAsync(hp, d, (size_t)items * width * es, s));
+        return NGB200_OK;
+    }
+    return fail(NGB200_ERR_INVALID, "host operand must be SoA (batch_stride 1) or packed AoS (comp_stride 1, batch_stride width)");
+}
+
+extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *in, const ngb200_operand *out,
+                                       const double *params, int64_t batch, int32_t device, int64_t chunk_items) {
+    if (!P || !out) return fail(NGB200_ERR_INVALID, "null argument");
+    if (P->any_indexed) return fail(NGB200_ERR_INVALID, "run_host does not support indexed operands");
+    int rc = need_driver();
+    if (rc) return rc;
+    int dev;
+    rc = current_device(&dev, device);
+    if (rc) return rc;
+    if (batch <= 0) return NGB200_OK;
+    const int es = esize(P->dtype);
+    const size_t nin = P->in_width.size(), nout = P->out_width.size();
+    int64_t per_item = 0;
+    for (size_t k = 0; k < nin; ++k) if (P->in_mode[k] == NGB200_VARYING) per_item += P->in_width[k] * es;
+    for (size_t k = 0; k < nout; ++k) per_item += P->out_width[k] * es;
+    if (chunk_items <= 0) chunk_items = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 64) * (1 << 20) / (per_item ? per_item : 1);
+    chunk_items = (chunk_items + 255) / 256 * 256;
+    if (chunk_items > batch) chunk_items = (batch + 255) / 256 * 256;
+    const int n_slots = (int)std::min<int64_t>(env_int("NGB200_HOST_STREAMS", 4), (batch + chunk_items - 1) / chunk_items);
+
+    HostRun run;
+    run.slots.resize(n_slots);
+    run.bcast.assign(nin, 0);
+    for (Slot &s : run.slots) {
+        CU(cuStreamCreate(&s.stream, CU_STREAM_NON_BLOCKING));
+        s.in.assign(nin, 0);
+        s.out.assign(nout, 0);
+        for (size_t k = 0; k < nin; ++k)
+            if (P->in_mode[k] == NGB200_VARYING && P->in_width[k]) CU(cuMemAlloc(&s.in[k], (size_t)chunk_items * P->in_width[k] * es));
+        for (size_t k = 0; k < nout; ++k)
+            if (P->out_width[k]) CU(cuMemAlloc(&s.out[k], (size_t)chunk_items * P->out_width[k] * es));
+    }
+    // broadcast operands: one small upload, visible to all streams after a sync
+    for (size_t k = 0; k < nin; ++k) {
+        if (P->in_mode[k] != NGB200_BROADCAST || !P->in_width[k]) continue;
+        CU(cuMemAlloc(&run.bcast[k], (size_t)P->in_width[k] * es));
+        std::vector<char> packed((size_t)P->in_width[k] * es);
+        for (int c = 0; c < P->in_width[k]; ++c) memcpy(&packed[(size_t)c * es], (char *)in[k].ptr + (size_t)c * in[k].comp_stride * es, es);
+        CU(cuMemcpyHtoDAsync(run.bcast[k], packed.data(), packed.size(), run.slots[0].stream));
+        CU(cuStreamSynchronize(run.slots[0].stream));
+    }
+    std::vector<ngb200_operand> din(nin ? nin : 1), dout(nout);
+    int64_t chunk_index = 0;
+    for (int64_t first = 0; first < batch; first += chunk_items, ++chunk_index) {
+        Slot &s = run.slots[chunk_index % n_slots];
+        int64_t items = std::min(chunk_items, batch - first);
+        for (size_t k = 0; k < nin; ++k) {
+            if (P->in_mode[k] == NGB200_BROADCAST) { din[k] = {(void *)run.bcast[k], 1, 0, nullptr}; continue; }
+            bool soa = in[k].batch_stride == 1;
+            rc = copy_chunk(true, in[k], P->in_width[k], es, first, items, s.in[k], chunk_items, s.stream);
+            if (rc) return rc;
+            din[k] = {(void *)s.in[k], soa ? chunk_items : 1, soa ? 1 : P->in_width[k], nullptr};
+        }
+        for (size_t k = 0; k < nout; ++k) {
+            bool soa = out[k].batch_stride == 1;
+            dout[k] = {(void *)s.out[k], soa ? chunk_items : 1, soa ? 1 : P->out_width[k], nullptr};
+        }
+        rc = ngb200_program_launch(P, din.data(), dout.data(), params, items, s.stream);
+        if (rc) return rc;
+        for (size_t k = 0; k < nout; ++k) {
+            rc = copy_chunk(false, out[k], P->out_width[k], es, first, items, s.out[k], chunk_items, s.stream);
+            if (rc) return rc;
+        }
+    }
+    for (Slot &s : run.slots) CU(cuStreamSynchronize(s.stream));
+    return NGB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// statically compiled helper kernel: counter-based normal generator for synthetic benchmarks
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&r)[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ngb_fill_normal_kernel(T *__restrict__ out, long long n, unsigned long long seed,
+                                                              unsigned long long offset, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
+        unsigned long long ctr = offset / 4 + (unsigned long long)q;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        float v[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+            float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
+            float rad = sqrtf(-2.0f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.283185307179586f * u2, &sn, &cs);
+            v[2 * h] = rad * cs * scale;
+            v[2 * h + 1] = rad * sn * scale;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (q * 4 + j < n) out[q * 4 + j] = (T)v[j];
+    }
+}
+
+extern "C" int ngb200_fill_normal(void *ptr, int64_t n, uint64_t seed, uint64_t offset, double scale, int32_t dtype,
+                                  void *stream) {
+    if (!ptr || n < 0 || offset % 4) return fail(NGB200_ERR_INVALID, "bad argument (offset must be a multiple of 4)");
+    if (n == 0) return NGB200_OK;
+    int64_t quads = (n + 3) / 4;
+    int blocks = (int)std::min<int64_t>((quads + 255) / 256, 148 * 8);
+    if (dtype == NGB200_F64)
+        ngb_fill_normal_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double *)ptr, n, seed, offset, (float)scale);
+    else
+        ngb_fill_normal_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float *)ptr, n, seed, offset, (float)scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(NGB200_ERR_CUDA, "fill_normal launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return NGB200_OK;
+}
+
+extern "C" const char *ngb200_version(void) {
+    static std::string v;
+    if (v.empty()) {
+        int maj = 0, min = 0;
+        nvrtcVersion(&maj, &min);
+        v = std::string("numga_b200 " NGB_VERSION " sm_100a nvrtc ") + std::to_string(maj) + "." + std::to_string(min);
+    }
+    return v.c_str();
+}

@@ -1,0 +1,195 @@
+"""ctypes binding of the C ABI in include/numga_b200.h (libnumga_b200.so, built in-tree).
+
+This is the only way Python reaches the GPU kernels.  There is no fallback: if the shared
+library is missing, importing this module raises; if there is no CUDA device, launching raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnumga_b200.so')
+
+F32, F64 = 0, 1
+FAST, FAITHFUL = 0, 1
+VARYING, BROADCAST, INDEXED = 0, 1, 2
+
+(OP_INPUT, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SQRT, OP_RSQRT, OP_RCP, OP_ABS,
+ OP_NAN_TO_NUM, OP_FMA, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_SELECT_GT0) = range(21)
+
+N_OPERANDS = {OP_INPUT: 0, OP_CONST: 0, OP_PARAM: 0, OP_NEG: 1, OP_SQRT: 1, OP_RSQRT: 1, OP_RCP: 1, OP_ABS: 1,
+              OP_EXP: 1, OP_LOG: 1, OP_SIN: 1, OP_COS: 1, OP_FMA: 3, OP_SELECT_GT0: 3}
+
+
+class NGB200Error(RuntimeError):
+    pass
+
+
+class Instr(C.Structure):
+    _fields_ = [('op', C.c_int32), ('a', C.c_int32), ('b', C.c_int32), ('c', C.c_int32)]
+
+
+class Store(C.Structure):
+    _fields_ = [('operand', C.c_int32), ('component', C.c_int32), ('value', C.c_int32)]
+
+
+class ProgramDesc(C.Structure):
+    _fields_ = [
+        ('dtype', C.c_int32), ('flags', C.c_uint32),
+        ('n_inputs', C.c_int32), ('input_width', C.POINTER(C.c_int32)), ('input_mode', C.POINTER(C.c_int32)),
+        ('n_outputs', C.c_int32), ('output_width', C.POINTER(C.c_int32)), ('output_mode', C.POINTER(C.c_int32)),
+        ('n_params', C.c_int32),
+        ('n_consts', C.c_int32), ('consts', C.POINTER(C.c_double)),
+        ('n_instr', C.c_int32), ('instr', C.POINTER(Instr)),
+        ('n_stores', C.c_int32), ('stores', C.POINTER(Store)),
+        ('vec', C.c_int32),
+    ]
+
+
+class Operand(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('comp_stride', C.c_int64), ('batch_stride', C.c_int64), ('index', C.c_void_p)]
+
+
+class ProgramInfo(C.Structure):
+    _fields_ = [('n_instr', C.c_int32), ('n_uniform', C.c_int32), ('vec', C.c_int32), ('regs_vec', C.c_int32),
+                ('regs_scalar', C.c_int32), ('cache_hit', C.c_int32), ('cubin_bytes', C.c_int64)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise NGB200Error(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(numga_b200 has no CPU fallback)')
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    sigs = {
+        'ngb200_version': (C.c_char_p, []),
+        'ngb200_last_error': (C.c_char_p, []),
+        'ngb200_set_cache_dir': (i32, [C.c_char_p]),
+        'ngb200_operator_create': (i32, [C.POINTER(i32), i32, i32, C.POINTER(i32), i32, i32, u32, u32, C.POINTER(vp)]),
+        'ngb200_program_create': (i32, [C.POINTER(ProgramDesc), C.POINTER(vp)]),
+        'ngb200_program_destroy': (None, [vp]),
+        'ngb200_program_get_info': (i32, [vp, C.POINTER(ProgramInfo)]),
+        'ngb200_program_source': (C.c_char_p, [vp]),
+        'ngb200_program_launch': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(C.c_double), i64, vp]),
+        'ngb200_program_run_host': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(C.c_double), i64, i32, i64]),
+        'ngb200_host_alloc': (i32, [C.POINTER(vp), i64]),
+        'ngb200_host_free': (i32, [vp]),
+        'ngb200_fill_normal': (i32, [vp, i64, u64, u64, C.c_double, i32, vp]),
+        'ngb200_launch_count': (i64, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib, tuple(sigs)
+
+
+lib, EXPORTED = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise NGB200Error(f'numga_b200 error {rc}: {lib.ngb200_last_error().decode()}')
+
+
+def version():
+    return lib.ngb200_version().decode()
+
+
+def launch_count():
+    return int(lib.ngb200_launch_count())
+
+
+def _i32(seq):
+    seq = list(seq)
+    return (C.c_int32 * max(len(seq), 1))(*seq)
+
+
+class Program:
+    """A compiled straight-line program (one kernel pair: 128-bit vectorised + generic strided)."""
+
+    def __init__(self, handle, in_width, in_mode, out_width, out_mode, n_params, dtype):
+        self.handle = C.c_void_p(handle)
+        self.in_width, self.in_mode = tuple(in_width), tuple(in_mode)
+        self.out_width, self.out_mode = tuple(out_width), tuple(out_mode)
+        self.n_params = n_params
+        self.dtype = dtype
+
+    @classmethod
+    def from_ir(cls, dtype, flags, in_width, in_mode, out_width, out_mode, n_params, consts, instr, stores, vec=0):
+        """instr: sequence of (op, a, b, c); stores: sequence of (operand, component, value)."""
+        d = ProgramDesc()
+        d.dtype, d.flags = dtype, flags
+        d.n_inputs = len(in_width)
+        iw, im = _i32(in_width), _i32(in_mode)
+        d.input_width, d.input_mode = iw, im
+        d.n_outputs = len(out_width)
+        ow, om = _i32(out_width), _i32(out_mode)
+        d.output_width, d.output_mode = ow, om
+        d.n_params = n_params
+        cs = (C.c_double * max(len(consts), 1))(*consts)
+        d.n_consts, d.consts = len(consts), cs
+        ins = (Instr * max(len(instr), 1))(*[Instr(*map(int, t)) for t in instr])
+        d.n_instr, d.instr = len(instr), ins
+        sts = (Store * max(len(stores), 1))(*[Store(*map(int, t)) for t in stores])
+        d.n_stores, d.stores = len(stores), sts
+        d.vec = vec
+        h = C.c_void_p()
+        check(lib.ngb200_program_create(C.byref(d), C.byref(h)))
+        return cls(h.value, in_width, in_mode, out_width, out_mode, n_params, dtype)
+
+    @classmethod
+    def from_terms(cls, terms, n_in, n_out, dtype, bcast_mask=0, flags=FAST):
+        """terms: int array [n_terms, arity + 2] rows (i_0 .. i_{k-1}, o, coeff) in precompute_sparse order."""
+        n_in = list(n_in)
+        arity = len(n_in)
+        terms = np.ascontiguousarray(np.asarray(terms, dtype=np.int32).reshape(-1, arity + 2))
+        h = C.c_void_p()
+        check(lib.ngb200_operator_create(
+            terms.ctypes.data_as(C.POINTER(C.c_int32)), len(terms), arity, _i32(n_in), n_out, dtype,
+            bcast_mask, flags, C.byref(h)))
+        modes = [BROADCAST if (bcast_mask >> k) & 1 else VARYING for k in range(arity)]
+        return cls(h.value, n_in, modes, [n_out], [VARYING], 0, dtype)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.ngb200_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def source(self):
+        return lib.ngb200_program_source(self.handle).decode()
+
+    @property
+    def info(self):
+        info = ProgramInfo()
+        check(lib.ngb200_program_get_info(self.handle, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in ProgramInfo._fields_}
+
+    @staticmethod
+    def _operands(specs):
+        arr = (Operand * max(len(specs), 1))()
+        for k, (ptr, cs, bs, *rest) in enumerate(specs):
+            arr[k] = Operand(ptr, cs, bs, rest[0] if rest else None)
+        return arr
+
+    def launch(self, inputs, outputs, batch, stream=0, params=()):
+        """inputs/outputs: sequences of (device_ptr, comp_stride, batch_stride[, index_ptr])."""
+        assert len(inputs) == len(self.in_width) and len(outputs) == len(self.out_width)
+        p = (C.c_double * max(len(params), 1))(*params)
+        check(lib.ngb200_program_launch(self.handle, self._operands(inputs), self._operands(outputs), p,
+                                        int(batch), C.c_void_p(stream)))
+
+    def run_host(self, inputs, outputs, batch, device=0, chunk_items=0, params=()):
+        """Same as launch, but with host pointers; synchronous."""
+        p = (C.c_double * max(len(params), 1))(*params)
+        check(lib.ngb200_program_run_host(self.handle, self._operands(inputs), self._operands(outputs), p,
+                                          int(batch), int(device), int(chunk_items)))
+
+
+def fill_normal(ptr, n, seed, offset=0, scale=1.0, dtype=F32, stream=0):
+    check(lib.ngb200_fill_normal(C.c_void_p(ptr), int(n), int(seed), int(offset), float(scale), dtype, C.c_void_p(stream)))

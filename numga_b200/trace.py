@@ -1,0 +1,390 @@
+"""Symbolic tracing of multivector code into the straight-line IR of include/numga_b200.h.
+
+`SymArray` stands in for the `values` array of a multivector while a function is traced: it has
+one SSA value per component and supports the arithmetic the multivector layer performs on
+`values` (`+ - * / **`, unary minus, `[..., i]`).  Batch axes are implicit: every traced
+operation is elementwise over the batch, which is exactly the structure of the hot path
+(numga/backend/numpy/operator.py:117-132 and the elementwise glue of
+numga/multivector/multivector.py:247-261,307-313,398-411).
+
+The `Trace` hash-conses instructions (common sub-expressions are shared) and applies only
+EXACT rewrites (x*1, x+0, -(-x), a-(-b) = a+b, constant folding in the program dtype), so the
+"faithful" programs stay bit-identical to evaluating the same chain op by op.
+"""
+import numpy as np
+
+from numga_b200 import runtime as rt
+
+
+class Trace:
+    def __init__(self, np_dtype, faithful=False):
+        self.np_dtype = np.dtype(np_dtype)
+        self.faithful = faithful
+        self.instr = []          # (op, a, b, c)
+        self.consts = []         # python floats, already rounded to dtype
+        self.uniform = []        # per value: depends only on broadcast inputs / consts / params
+        self.memo = {}
+        self.input_width, self.input_mode = [], []
+        self.n_params = 0
+
+    # ---- leaves ---------------------------------------------------------------------------------
+    def _push(self, key, uniform):
+        if key in self.memo:
+            return self.memo[key]
+        self.instr.append(key)
+        self.uniform.append(uniform)
+        self.memo[key] = len(self.instr) - 1
+        return self.memo[key]
+
+    def add_input(self, width, mode):
+        k = len(self.input_width)
+        self.input_width.append(int(width))
+        self.input_mode.append(int(mode))
+        return [self._push((rt.OP_INPUT, k, c, 0), mode == rt.BROADCAST) for c in range(width)]
+
+    def add_param(self):
+        k = self.n_params
+        self.n_params += 1
+        return self._push((rt.OP_PARAM, k, 0, 0), True)
+
+    def const(self, value):
+        v = float(self.np_dtype.type(value))
+        key = ('const', v if v == v else 'nan', np.signbit(v))
+        if key in self.memo:
+            return self.memo[key]
+        self.consts.append(v)
+        vid = self._push((rt.OP_CONST, len(self.consts) - 1, 0, 0), True)
+        self.memo[key] = vid
+        return vid
+
+    def const_value(self, vid):
+        op, a, _, _ = self.instr[vid]
+        return self.consts[a] if op == rt.OP_CONST else None
+
+    def is_const(self, vid, value):
+        c = self.const_value(vid)
+        return c is not None and c == value and not (value == 0 and np.signbit(c))
+
+    def _neg_of(self, vid):
+        op, a, _, _ = self.instr[vid]
+        return a if op == rt.OP_NEG else None
+
+    def _fold(self, fn, *vids):
+        vals = [self.const_value(v) for v in vids]
+        if any(v is None for v in vals):
+            return None
+        t = self.np_dtype.type
+        with np.errstate(all='ignore'):
+            return self.const(fn(*[t(v) for v in vals]))
+
+    def _emit(self, op, a=0, b=0, c=0):
+        n = rt.N_OPERANDS.get(op, 2)
+        u = all(self.uniform[x] for x in (a, b, c)[:n])
+        return self._push((op, a, b, c), u)
+
+    # ---- arithmetic with exact simplifications ------------------------------------------------------
+    def neg(self, a):
+        f = self._fold(lambda x: -x, a)
+        if f is not None:
+            return f
+        inner = self._neg_of(a)
+        return inner if inner is not None else self._emit(rt.OP_NEG, a)
+
+    def add(self, a, b):
+        f = self._fold(lambda x, y: x + y, a, b)
+        if f is not None:
+            return f
+        if self.is_const(a, 0.0):
+            return b
+        if self.is_const(b, 0.0):
+            return a
+        nb = self._neg_of(b)
+        if nb is not None:
+            return self.sub(a, nb)
+        na = self._neg_of(a)
+        if na is not None:
+            return self.sub(b, na)
+        return self._emit(rt.OP_ADD, min(a, b), max(a, b))
+
+    def sub(self, a, b):
+        f = self._fold(lambda x, y: x - y, a, b)
+        if f is not None:
+            return f
+        if self.is_const(b, 0.0):
+            return a
+        if self.is_const(a, 0.0):
+            return self.neg(b)
+        nb = self._neg_of(b)
+        if nb is not None:
+            return self.add(a, nb)
+        return self._emit(rt.OP_SUB, a, b)
+
+    def mul(self, a, b):
+        f = self._fold(lambda x, y: x * y, a, b)
+        if f is not None:
+            return f
+        for x, y in ((a, b), (b, a)):
+            if self.is_const(x, 1.0):
+                return y
+            if self.is_const(x, -1.0):
+                return self.neg(y)
+            if self.is_const(x, 0.0):
+                return x
+        na, nb = self._neg_of(a), self._neg_of(b)
+        if na is not None and nb is not None:
+            return self.mul(na, nb)
+        if na is not None:
+            return self.neg(self.mul(na, b))
+        if nb is not None:
+            return self.neg(self.mul(a, nb))
+        return self._emit(rt.OP_MUL, min(a, b), max(a, b))
+
+    def div(self, a, b):
+        f = self._fold(lambda x, y: x / y, a, b)
+        if f is not None:
+            return f
+        if self.is_const(b, 1.0):
+            return a
+        if self.is_const(a, 1.0):
+            return self._emit(rt.OP_RCP, b)
+        return self._emit(rt.OP_DIV, a, b)
+
+    def unary(self, op, a, fn=None):
+        if fn is not None:
+            f = self._fold(fn, a)
+            if f is not None:
+                return f
+        return self._emit(op, a)
+
+    def sqrt(self, a):
+        return self.unary(rt.OP_SQRT, a, np.sqrt)
+
+    def rsqrt(self, a):
+        return self.unary(rt.OP_RSQRT, a, lambda x: 1 / np.sqrt(x))
+
+    def abs(self, a):
+        return self.unary(rt.OP_ABS, a, np.abs)
+
+    def nan_to_num(self, a, nan):
+        return self._emit(rt.OP_NAN_TO_NUM, a, self.const(nan))
+
+    def power(self, a, p):
+        if p == 0.5:
+            return self.sqrt(a)
+        if p == -0.5:
+            return self.rsqrt(a)
+        if p == 1:
+            return a
+        if p == -1:
+            return self.div(self.const(1.0), a)
+        if p == 2:
+            return self.mul(a, a)
+        raise NotImplementedError(f'power {p} is not supported in traced code')
+
+    # ---- output ----------------------------------------------------------------------------------------
+    def finish(self, outputs):
+        """outputs: list of lists of value ids (one list per output multivector). Returns IR pieces
+        with dead code removed and values renumbered."""
+        live = set()
+        stack = [v for out in outputs for v in out]
+        while stack:
+            v = stack.pop()
+            if v in live:
+                continue
+            live.add(v)
+            op, a, b, c = self.instr[v]
+            stack.extend((a, b, c)[:rt.N_OPERANDS.get(op, 2)])
+        order = sorted(live)
+        renum = {v: k for k, v in enumerate(order)}
+        used_consts, instr = {}, []
+        for v in order:
+            op, a, b, c = self.instr[v]
+            n = rt.N_OPERANDS.get(op, 2)
+            if op == rt.OP_CONST:
+                a = used_consts.setdefault(a, len(used_consts))
+            elif n:
+                a, b, c = [renum[x] if k < n else 0 for k, x in enumerate((a, b, c))]
+            instr.append((op, a, b, c))
+        consts = [None] * len(used_consts)
+        for old, new in used_consts.items():
+            consts[new] = self.consts[old]
+        stores = [(k, c, renum[v]) for k, out in enumerate(outputs) for c, v in enumerate(out)]
+        return dict(instr=instr, consts=consts, stores=stores, out_width=[len(o) for o in outputs],
+                    in_width=list(self.input_width), in_mode=list(self.input_mode), n_params=self.n_params)
+
+
+class SymArray:
+    """Symbolic stand-in for a multivector's `values` array ([..., n], batch axes implicit)."""
+
+    def __init__(self, trace: Trace, regs):
+        self.trace = trace
+        self.regs = list(regs)
+
+    @property
+    def shape(self):
+        return (Ellipsis, len(self.regs))
+
+    def __len__(self):
+        return len(self.regs)
+
+    def copy(self):
+        return SymArray(self.trace, self.regs)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            if len(idx) == 2 and idx[0] is Ellipsis:
+                idx = idx[1]
+            else:
+                raise IndexError('traced values support [..., i] / [..., a:b] only')
+        if idx is None:
+            return self
+        if isinstance(idx, slice):
+            return SymArray(self.trace, self.regs[idx])
+        if isinstance(idx, (list, np.ndarray)):
+            return SymArray(self.trace, [self.regs[int(i)] for i in idx])
+        return SymArray(self.trace, [self.regs[int(idx)]])
+
+    def _other(self, other):
+        if isinstance(other, SymArray):
+            assert other.trace is self.trace
+            regs = other.regs
+        elif isinstance(other, (int, float, np.floating, np.integer)):
+            regs = [self.trace.const(other)]
+        else:
+            arr = np.asarray(other)
+            if arr.dtype == object:
+                return None
+            regs = [self.trace.const(v) for v in arr.reshape(-1)]
+        n = max(len(regs), len(self.regs))
+        mine = self.regs * n if len(self.regs) == 1 else self.regs
+        regs = regs * n if len(regs) == 1 else regs
+        assert len(mine) == len(regs) == n, 'component counts do not broadcast'
+        return mine, regs
+
+    def _binary(self, other, fn, swap=False):
+        pair = self._other(other)
+        if pair is None:
+            return NotImplemented
+        a, b = pair
+        if swap:
+            a, b = b, a
+        return SymArray(self.trace, [fn(x, y) for x, y in zip(a, b)])
+
+    def __add__(self, o): return self._binary(o, self.trace.add)
+    def __radd__(self, o): return self._binary(o, self.trace.add, swap=True)
+    def __sub__(self, o): return self._binary(o, self.trace.sub)
+    def __rsub__(self, o): return self._binary(o, self.trace.sub, swap=True)
+    def __mul__(self, o): return self._binary(o, self.trace.mul)
+    def __rmul__(self, o): return self._binary(o, self.trace.mul, swap=True)
+    def __truediv__(self, o): return self._binary(o, self.trace.div)
+    def __rtruediv__(self, o): return self._binary(o, self.trace.div, swap=True)
+    def __neg__(self): return SymArray(self.trace, [self.trace.neg(r) for r in self.regs])
+    def __pos__(self): return self
+    def __pow__(self, p): return SymArray(self.trace, [self.trace.power(r, p) for r in self.regs])
+    def __abs__(self): return SymArray(self.trace, [self.trace.abs(r) for r in self.regs])
+
+    def map(self, fn):
+        return SymArray(self.trace, [fn(r) for r in self.regs])
+
+
+# ---- lowering of a symbolic operator applied to traced operands ---------------------------------------
+
+def lower_operator(trace: Trace, operator, inputs):
+    """Append `operator(*inputs)` to the trace; inputs are lists of value ids per argument.
+    Returns the value ids of the output components (implicit zeros for rows without terms)."""
+    zero = None
+    out = []
+    rows = dict(operator.precompute_sparse)
+    for o in range(len(operator.output)):
+        terms = rows.get(o)
+        if not terms:
+            zero = trace.const(0.0) if zero is None else zero
+            out.append(zero)
+        elif trace.faithful:
+            out.append(_row_faithful(trace, terms, inputs))
+        else:
+            out.append(_row_fast(trace, [(c, [inputs[k][i] for k, i in enumerate(idx)]) for idx, c in terms]))
+    return out
+
+
+def _row_faithful(trace, terms, inputs):
+    """Terms in precompute_sparse order; each product rounded factor by factor, then a sequential sum:
+    the order in which numpy's einsum accumulates (hard part 1)."""
+    acc = None
+    for idx, c in terms:
+        prod = None
+        for k in reversed(range(len(idx))):     # right-associated: a0 * (a1 * a2), einsum's contraction order
+            prod = inputs[k][idx[k]] if prod is None else trace.mul(inputs[k][idx[k]], prod)
+        if abs(c) != 1:
+            prod = trace.mul(prod, trace.const(abs(c)))
+        if acc is None:
+            acc = prod if c > 0 else trace.neg(prod)
+        else:
+            acc = trace.add(acc, prod) if c > 0 else trace.sub(acc, prod)
+    return acc
+
+
+def _row_fast(trace, terms):
+    """sum_t c_t * prod(factors_t), arranged for few multiplies:
+      * factors that are uniform over the batch are multiplied first and their partial sums are
+        shared, so a broadcast operand is pre-contracted once per thread (sandwich -> 4x4 matrix);
+      * products are built in a canonical order so twin terms of a repeated argument
+        (R_i R_k and R_k R_i) become one value with a summed integer coefficient;
+      * the sum is factored over the last remaining varying factor (Horner-like)."""
+    # merge identical products
+    merged = {}
+    for c, factors in terms:
+        key = tuple(sorted(factors))
+        merged[key] = merged.get(key, 0) + c
+    groups = {}   # varying factor tuple -> list of (coeff, uniform factor tuple)
+    for key, c in merged.items():
+        if c == 0:
+            continue
+        uni = tuple(f for f in key if trace.uniform[f])
+        var = tuple(f for f in key if not trace.uniform[f])
+        groups.setdefault(var, []).append((c, uni))
+
+    def signed_sum(items):
+        """items: list of (int coeff, value id or None for 1) -> value id"""
+        acc = None
+        for c, v in sorted(items, key=lambda t: (t[1] is None, t[1] if t[1] is not None else 0)):
+            if v is None:
+                term = trace.const(c)
+                sign = 1
+            else:
+                term = v if abs(c) == 1 else trace.mul(v, trace.const(abs(c)))
+                sign = 1 if c > 0 else -1
+            if acc is None:
+                acc = term if sign > 0 else trace.neg(term)
+            else:
+                acc = trace.add(acc, term) if sign > 0 else trace.sub(acc, term)
+        return acc
+
+    def product(factors):
+        acc = None
+        for f in factors:
+            acc = f if acc is None else trace.mul(acc, f)
+        return acc
+
+    # one coefficient (uniform) per varying product
+    partial = []
+    for var, items in groups.items():
+        coef = signed_sum([(c, product(uni) if uni else None) for c, uni in items])
+        partial.append((var, coef))
+    # factor over the least-shared varying factor: pick the factor position whose removal leaves
+    # the most repeated remainders -> here: group by the last factor (highest value id)
+    by_pivot = {}
+    for var, coef in partial:
+        if not var:
+            by_pivot.setdefault(None, []).append(((), coef))
+        else:
+            by_pivot.setdefault(var[-1], []).append((var[:-1], coef))
+    acc = None
+    for pivot in sorted(by_pivot, key=lambda p: -1 if p is None else p):
+        inner = None
+        for rest, coef in by_pivot[pivot]:
+            t = coef if not rest else trace.mul(product(rest), coef)
+            inner = t if inner is None else trace.add(inner, t)
+        term = inner if pivot is None else trace.mul(inner, pivot)
+        acc = term if acc is None else trace.add(acc, term)
+    return acc
