@@ -1,0 +1,105 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol the header declares, compiles
+kernels for sm_100a, and FAILS LOUDLY (no CPU fallback) when asked to launch without a device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from numga_b200 import runtime as rt
+from numga_b200.algebra import Algebra
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'numga_b200.h')
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ngb200_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ctypes.CDLL(rt.LIB_PATH)
+    declared = _declared()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/numga_b200.h but not exported'
+    assert set(rt.EXPORTED) == set(declared), 'runtime.py binds a different set of symbols than the header declares'
+
+
+def test_library_contains_sm100a_code_and_no_driver_link_dependency():
+    out = subprocess.run(['cuobjdump', '-lelf', rt.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    needed = subprocess.run(['readelf', '-d', rt.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'libcuda.so' not in needed      # the driver is dlopen()ed at first launch, so this loads on CPU boxes
+
+
+def test_version_string():
+    assert rt.version().startswith('numga_b200 ') and 'sm_100a' in rt.version()
+
+
+def _terms(op):
+    return np.concatenate([op.index, op.coeff[:, None]], axis=1)
+
+
+def test_operator_kernel_compiles_without_gpu_and_is_vectorised():
+    a = Algebra.from_pqr(3, 0, 1)
+    M = a.subspace.even_grade()
+    prog = rt.Program.from_terms(_terms(a.operator.product(M, M)), [8, 8], 8, rt.F32)
+    info = prog.info
+    assert info['vec'] == 4 and info['n_instr'] == 88 and info['cubin_bytes'] > 0
+    src = prog.source
+    assert 'float4' in src and 'ngb_vec' in src and 'ngb_scalar' in src
+
+
+def test_generated_sass_uses_128bit_global_accesses(tmp_path):
+    a = Algebra.from_pqr(3, 0, 1)
+    M = a.subspace.even_grade()
+    os.environ['NGB200_CACHE_DIR'] = str(tmp_path)
+    try:
+        rt.check(rt.lib.ngb200_set_cache_dir(str(tmp_path).encode()))
+        rt.Program.from_terms(_terms(a.operator.product(M, M)), [8, 8], 8, rt.F32)
+        cubins = [f for f in os.listdir(tmp_path) if f.endswith('.cubin')]
+        assert len(cubins) == 1
+        sass = subprocess.run(['cuobjdump', '-sass', os.path.join(tmp_path, cubins[0])], capture_output=True, text=True).stdout
+        assert sass.count('LDG.E.128') >= 16 and sass.count('STG.E.128') >= 8
+    finally:
+        del os.environ['NGB200_CACHE_DIR']
+        rt.check(rt.lib.ngb200_set_cache_dir(b''))
+
+
+def test_bad_descriptions_are_rejected_with_a_message():
+    with pytest.raises(rt.NGB200Error, match='out of range'):
+        rt.Program.from_terms([[9, 0, 0, 1]], [8, 8], 8, rt.F32)
+    with pytest.raises(rt.NGB200Error, match='operand'):
+        rt.Program.from_ir(rt.F32, rt.FAST, [2], [0], [1], [0], 0, [], [(rt.OP_INPUT, 0, 0, 0), (rt.OP_ADD, 0, 5, 0)], [(0, 0, 1)])
+    with pytest.raises(rt.NGB200Error, match='dtype'):
+        rt.Program.from_ir(7, rt.FAST, [2], [0], [1], [0], 0, [], [(rt.OP_INPUT, 0, 0, 0)], [(0, 0, 0)])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_launch_without_gpu_fails_loudly():
+    a = Algebra.from_pqr(3, 0, 1)
+    M = a.subspace.even_grade()
+    prog = rt.Program.from_terms(_terms(a.operator.product(M, M)), [8, 8], 8, rt.F32)
+    x = np.zeros((8, 16), np.float32)
+    with pytest.raises(rt.NGB200Error, match='no CPU fallback'):
+        prog.launch([(x.ctypes.data, 16, 1)] * 2, [(x.ctypes.data, 16, 1)], 16)
+    from numga_b200 import B200Context
+    ctx = B200Context((3, 0, 1), device='cpu')
+    m = ctx.multivector.motor(np.ones((4, 8), np.float32))
+    with pytest.raises(rt.NGB200Error, match='no CPU path'):
+        m * m
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'numga_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in text.replace('numga_oracle', 'oracle') or f == 'ngb200.cu' and 'oracle' not in text, \
+                    f'{f} mentions the oracle: product code must not depend on it'

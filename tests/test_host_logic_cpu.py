@@ -1,0 +1,99 @@
+"""Host-side logic that needs no GPU: subspace predicates and dispatch, storage layout helpers, the
+compile-only execution of the whole case catalogue (eager + fused), API surface."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES
+from numga_b200 import B200Context
+from numga_b200.backend import flat_operand, soa_empty, to_soa
+
+
+def test_dispatch_predicates_3dpga():
+    ctx = B200Context((3, 0, 1), device='cpu')
+    S = ctx.subspace
+    M = S.even_grade()
+    assert M.symmetric_reverse().named_str == '1,abcd' and M.symmetric_reverse().is_study
+    assert S.vector().symmetric_reverse().equals.scalar()
+    assert S.bivector().degenerate().is_degenerate and not S.bivector().is_degenerate
+    assert S.translator().named_str == '1,ad,bd,cd' and S.translator().is_degenerate_scalar
+    assert S.bireflection().named_str == '1,ab,ac,bc,ad,bd,cd'
+    assert M.is_subalgebra and not S.vector().is_subalgebra
+    assert S.vector().simplicity == 1 and M.simplicity == 2 and S.scalar().simplicity == 0
+    assert (S.scalar().union(S.bivector())) is S.bireflection()       # flyweight identity
+    assert S.xy_zw if False else S.ab_cd.named_str == 'ab,cd'
+
+
+def test_soa_layout_and_flattening():
+    v = soa_empty(8, (1000,), torch.float32, 'cpu')
+    assert v.shape == (1000, 8) and v.stride() == (1, 1024)           # row pitch padded to 128 bytes
+    t, ptr, cs, bs = flat_operand(v, 1000)
+    assert (cs, bs) == (1024, 1) and ptr % 16 == 0
+    w = soa_empty(4, (3, 5), torch.float32, 'cpu')
+    assert w.shape == (3, 5, 4) and flat_operand(w, 15)[2:] == (15, 1)
+    aos = torch.arange(40.).reshape(10, 4)
+    s = to_soa(aos)
+    assert torch.equal(s, aos) and s.stride() == (1, 32)
+    sliced = s[::2]                                                     # strided batch still flattens
+    assert flat_operand(sliced, 5)[2:] == (32, 2)
+    single = torch.zeros(8)
+    assert flat_operand(single, 1)[3] == 0
+
+
+def test_coerce_array_converts_aos_to_soa():
+    ctx = B200Context((3, 0, 1), device='cpu')
+    m = ctx.multivector.motor(np.arange(80, dtype=np.float32).reshape(10, 8))
+    assert m.values.shape == (10, 8) and m.values.stride(0) == 1 and m.shape == (10,)
+    assert np.array_equal(m.numpy(), np.arange(80, dtype=np.float32).reshape(10, 8))
+    unit = ctx.multivector.motor()
+    assert unit.numpy().tolist() == [1, 0, 0, 0, 0, 0, 0, 0]
+    with pytest.raises(AssertionError):
+        ctx.multivector.motor(np.zeros((3, 7), np.float32))
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_whole_catalogue_runs_in_compile_only_mode(case):
+    """Every case executes eagerly (one kernel per method) and fused (one kernel) with the right output
+    subspace and batch shape; kernels are compiled for sm_100a, nothing is launched."""
+    name, pqr, specs, scale, fn = case
+    ctx = B200Context(pqr, device='cpu', compile_only=True)
+    mvs = []
+    for sub, kind in specs:
+        s = getattr(ctx.subspace, sub)()
+        mvs.append(ctx.multivector(values=torch.zeros((5, len(s)) if kind == 'batch' else (len(s),)), subspace=s))
+    eager = fn(*mvs)
+    fused = ctx.jit(fn)(*mvs)
+    assert eager.subspace is fused.subspace
+    assert eager.shape == fused.shape == (5,)
+    assert eager.values.shape[-1] == len(eager.subspace)
+
+
+def test_jit_cache_keys_on_subspace_and_broadcast_pattern():
+    ctx = B200Context((3, 0, 1), device='cpu', compile_only=True)
+    f = ctx.jit(lambda r, p: r >> p)
+    R1, Rn = ctx.multivector.motor(torch.zeros(8)), ctx.multivector.motor(torch.zeros(6, 8))
+    p = ctx.multivector.antivector(torch.zeros(6, 4))
+    v = ctx.multivector.vector(torch.zeros(6, 4))
+    f(R1, p); n1 = len(ctx.engine.cache)
+    f(R1, p); assert len(ctx.engine.cache) == n1
+    f(Rn, p); assert len(ctx.engine.cache) == n1 + 1
+    f(R1, v); assert len(ctx.engine.cache) == n1 + 2
+    scaled = ctx.jit(lambda m, s: m * s)
+    scaled(Rn, 2.0); n2 = len(ctx.engine.cache)
+    scaled(Rn, 3.5); assert len(ctx.engine.cache) == n2          # python scalars are runtime parameters
+
+
+def test_multivector_data_movement_api():
+    ctx = B200Context((3, 0, 1), device='cpu', compile_only=True)
+    m = ctx.multivector.motor(torch.arange(48.).reshape(6, 8))
+    assert m[2:4].shape == (2,) and len(m) == 6
+    assert m.concatenate(m, axis=0).shape == (12,)
+    assert m.reshape((2, 3)).shape == (2, 3) and m.reshape((2, 3)).flatten().shape == (6,)
+    assert m.sum(axis=0).shape == ()
+    upd = m.at[0].set(torch.ones(8))
+    assert upd.values[0].tolist() == [1.0] * 8 and m.values[0, 1].item() == 1.0
+    assert m.select.bivector().subspace is ctx.subspace.bivector()
+    assert m.restrict[2].subspace is ctx.subspace.bivector()
+    assert m.select[1].subspace is ctx.subspace.vector()
+    assert (m + 1).subspace is m.subspace and (1 + m.select.bivector()).subspace is ctx.subspace.bireflection()
+    assert ctx.multivector.ab.subspace.named_str == 'ab'
