@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (see BASELINE.json): batched multivector products on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs]
+
+Headline workload (BASELINE.json configs[1]): 3D PGA (3,0,1), sandwich R >> p of 2^28 points with ONE
+broadcast motor, fp32.  A step = one pass of the generated kernel over the batch.  One process per GPU
+(torchrun for N > 1); the batch axis is sharded with no collective on the data path ("weak": every GPU
+processes its own 2^28-point slice).  Prints ONE JSON line on rank 0.
+
+  value          points/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            same metric through the C-ABI host-buffer call (ngb200_program_run_host): pinned host inputs,
+                 H2D + kernel + D2H inside the timed region
+  roofline       algorithmic bytes (32 B/point) / kernel time vs the measured copy bandwidth
+  cpu_baseline   the oracle (numpy einsum restatement of the reference's numpy backend) on the host cores
+  configs        (with --configs) the other BASELINE.json configurations, device timed, each with its roofline
+
+`--impl reference` times the reference's CPU algorithm (oracle port; the reference is a Python package that
+cannot travel to the GPU box) on all host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POINTS_PER_GPU = 1 << 28
+BYTES_PER_POINT = 32          # 4 components read + 4 written, fp32; the broadcast motor counts 0
+METRIC = 'multivector products/sec (3D PGA motor sandwich R >> p, broadcast motor, fp32)'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(n_points, seed):
+    from oracle import numga_oracle as O
+    alg = O.Algebra((3, 0, 1))
+    rng = np.random.default_rng(seed)
+    _W['R'] = O.MV.make(alg, 'even_grade', rng.standard_normal(8), np.float32)
+    _W['p'] = O.MV.make(alg, 'antivector', rng.standard_normal((n_points, 4)), np.float32)
+    _W['R'] >> _W['p']          # builds and caches the integer tables
+
+
+def _cpu_worker_step(_):
+    t = time.perf_counter()
+    out = _W['R'] >> _W['p']
+    return time.perf_counter() - t, float(out.values[0, 0])
+
+
+def cpu_reference(steps, warmup, points_per_worker=1 << 22, max_workers=64):
+    """Reference algorithm on the host: numpy einsum is single-threaded, so one process per core, each with
+    its own slice (the same sharding the GPUs use). Returns (points/s, cores, sample description, ms/step)."""
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, max_workers))
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(points_per_worker, 1)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_worker_step, range(cores))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_worker_step, range(cores))
+        dt = (time.perf_counter() - t0) / steps
+    total = points_per_worker * cores
+    return total / dt, cores, f'{cores} processes x 2^{int(np.log2(points_per_worker))} points per step (oracle port of the numpy backend, einsum optimize=True, order=F)', dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    value, cores, sample, ms = cpu_reference(max(1, args.steps), max(1, args.warmup))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE.json configs[1]: 3D PGA (3,0,1) R >> p, broadcast motor, fp32 (bounded CPU sample per step)'},
+        'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------------------
+def device_mv(ctx, sub, n, seed, rank, scale=1.0):
+    """Synthetic multivector batch generated ON the device: every rank fills its own slice of one
+    counter-based normal stream (offset = rank * n), component rows are independent streams."""
+    import torch
+    from numga_b200 import runtime as rt
+    from numga_b200.backend import soa_empty
+    v = soa_empty(len(sub), (n,), ctx.dtype, ctx.device)
+    rows = v.movedim(-1, 0)
+    dt = rt.F32 if ctx.dtype == torch.float32 else rt.F64
+    for c in range(len(sub)):
+        rt.fill_normal(rows[c].data_ptr(), n, seed=seed * 1000 + c, offset=rank * n, scale=scale, dtype=dt,
+                       stream=torch.cuda.current_stream().cuda_stream)
+    return ctx.multivector(values=v, subspace=sub)
+
+
+def time_steps(fn, steps, warmup, dist=None):
+    """CUDA-event timing on the launching stream, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
+def other_configs(torch, B200Context, rank, peak):
+    """The remaining BASELINE.json configurations on one GPU, device timed (supplementary)."""
+    out = []
+
+    def entry(name, unit_bytes, n, ms, flops=None, note=None):
+        gbs = unit_bytes * n / ms / 1e6
+        e = {'config': name, 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': unit_bytes,
+             'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak}
+        if flops:
+            e['tflops'] = flops * n / ms / 1e9
+        if note:
+            e['note'] = note
+        out.append(e)
+
+    pga = B200Context((3, 0, 1), dtype=torch.float32)
+    S = pga.subspace
+    for n, tag in ((1 << 20, 'config 1: motor*motor, batch 2^20 (96 MB: L2-resident between launches)'),
+                   (1 << 26, 'config 1: motor*motor, batch 2^26')):
+        a, b = device_mv(pga, S.even_grade(), n, 11, rank), device_mv(pga, S.even_grade(), n, 12, rank)
+        ms = time_steps(lambda: a * b, 20, 3)
+        entry(tag, 96, n, ms, flops=88)
+        del a, b
+    for dtype, tag, ub in ((torch.float32, 'fp32', 48), (torch.float64, 'fp64', 96)):
+        c = B200Context((3, 0, 1), dtype=dtype)
+        n = 1 << 28 if dtype == torch.float32 else 1 << 27
+        bv = device_mv(c, c.subspace.bivector(), n, 13, rank, scale=0.5)
+        f = c.jit(lambda x: x.exp().normalized().motor_log())
+        ms = time_steps(lambda: f(bv), 5, 2)
+        prog = c.engine.cache[next(k for k in c.engine.cache if k[0][0] == 'jit')].program
+        entry(f'config 3: exp->normalized->motor_log fused round trip, {tag}, batch 2^{int(np.log2(n))}', ub, n, ms,
+              flops=prog.info['n_instr'], note='compute-bound: one kernel, all intermediates in registers; flops = live IR instructions')
+        del bv
+    cga = B200Context((4, 1, 0), dtype=torch.float32)
+    F = cga.subspace.full()
+    n = 1 << 26
+    x, y = device_mv(cga, F, n, 14, rank), device_mv(cga, F, n, 15, rank)
+    ms = time_steps(lambda: x * y, 10, 3)
+    entry('config 4: CGA (4,1,0) full*full geometric product, batch 2^26 (SIMT, 1024 FMA/item)', 384, n, ms, flops=2016)
+    return out
+
+
+def run_ours(args):
+    import torch
+    from numga_b200 import B200Context, runtime as rt
+
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (numga_b200 has no CPU path); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    peak, peak_src = measured_peaks()
+    n = args.points
+    ctx = B200Context((3, 0, 1), dtype=torch.float32, device=f'cuda:{local}')
+    S = ctx.subspace
+    R = ctx.multivector.motor(np.random.default_rng(1).standard_normal(8).astype(np.float32)).normalized()
+    p = device_mv(ctx, S.antivector(), n, seed=2, rank=rank)
+    sandwich = ctx.jit(lambda r, x: r >> x)
+    sandwich(R, p)
+    torch.cuda.synchronize()
+
+    launches0 = rt.launch_count()
+    with ClockSampler(local) as clocks:
+        ms = time_steps(lambda: sandwich(R, p), args.steps, args.warmup, dist)
+    launches = (rt.launch_count() - launches0) - args.warmup        # launches inside the timed region
+    clock_summary = clocks.summary()
+    value = world * n / ms * 1e3
+    achieved = BYTES_PER_POINT * n / ms / 1e6
+
+    # ---- end to end through the C-ABI host-buffer call ---------------------------------------------------------
+    import ctypes
+    prog = ctx.engine.cache[next(k for k in ctx.engine.cache if k[0][0] == 'jit')].program
+    e2e_n = n
+    try:
+        import psutil
+        if psutil.virtual_memory().available < 6 * 2 * 16 * n * max(1, min(world, 8)):
+            e2e_n = n // 8
+    except Exception:
+        pass
+    hin, hout, hR = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    rt.check(rt.lib.ngb200_host_alloc(ctypes.byref(hin), 16 * e2e_n))
+    rt.check(rt.lib.ngb200_host_alloc(ctypes.byref(hout), 16 * e2e_n))
+    rt.check(rt.lib.ngb200_host_alloc(ctypes.byref(hR), 32))
+    host_p = np.ctypeslib.as_array(ctypes.cast(hin, ctypes.POINTER(ctypes.c_float)), shape=(4, e2e_n))
+    host_q = np.ctypeslib.as_array(ctypes.cast(hout, ctypes.POINTER(ctypes.c_float)), shape=(4, e2e_n))
+    host_R = np.ctypeslib.as_array(ctypes.cast(hR, ctypes.POINTER(ctypes.c_float)), shape=(8,))
+    host_R[:] = R.numpy()
+    chunk = 1 << 22
+    for i in range(0, e2e_n, chunk):        # pinned host input: a copy of the device data (SoA, as numpy order='F')
+        host_p[:, i:i + chunk] = p.values[i:i + chunk].T.cpu().numpy()
+    ins = [(hR.value, 1, 0), (hin.value, e2e_n, 1)]
+    outs = [(hout.value, e2e_n, 1)]
+    e2e_steps = max(1, min(args.steps, 4))
+    prog.run_host(ins, outs, e2e_n, device=local)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prog.run_host(ins, outs, e2e_n, device=local)           # synchronous: returns when outputs are on the host
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    check = sandwich(R, p).values[:1 << 16].T.cpu().numpy()
+    e2e_ok = bool(np.array_equal(check, host_q[:, :1 << 16]))
+    e2e = {'value': world * e2e_n / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': 16 * e2e_n + 32,
+           'd2h_bytes_per_step': 16 * e2e_n, 'steps': e2e_steps, 'points_per_gpu': e2e_n,
+           'matches_device_result': e2e_ok, 'path': 'ngb200_program_run_host (pinned host SoA buffers, chunked H2D/kernel/D2H over 4 streams)'}
+    for h in (hin, hout, hR):
+        rt.lib.ngb200_host_free(h)
+
+    # ---- optional final gather over NVLink (not on the hot path; timed separately) ------------------------------
+    gather = None
+    if dist is not None:
+        gn = 1 << 24
+        src = sandwich(R, p).values[:gn].movedim(-1, 0).contiguous()
+        dst = torch.empty((world,) + tuple(src.shape), device='cuda', dtype=src.dtype)
+        g_ms = time_steps(lambda: dist.all_gather_into_tensor(dst, src), 5, 2, dist)
+        gather = {'bytes_per_rank': src.numel() * 4, 'ms': g_ms, 'algbw_gbs': src.numel() * 4 * (world - 1) / g_ms / 1e6,
+                  'note': 'NCCL all_gather of a 2^24-point output slice per rank; results stay sharded by default'}
+
+    line = None
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'r01_sandwich_traffic.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'BASELINE.json configs[1]: 3D PGA (3,0,1) motor sandwich R >> p, one broadcast motor, fp32',
+                       'points_per_gpu': n, 'layout': 'structure-of-arrays [4, n] in HBM', 'parallelism': f'batch-sharded x{world}, no collective',
+                       'l2': f'inputs+outputs {2 * 16 * n / 1e9:.1f} GB per GPU per step >> 126 MB L2 (no flush needed)'},
+            'clocks': clock_summary, 'gpu_launches': launches, 'e2e': e2e,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': BYTES_PER_POINT * n, 'kernel_ms': ms},
+        }
+        if gather:
+            line['gather'] = gather
+    if args.configs and world == 1:
+        line['configs'] = other_configs(torch, B200Context, rank, peak)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample, _ = cpu_reference(3, 1)
+        line['cpu_baseline'] = {'value': v, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--points', type=int, default=POINTS_PER_GPU, help='points per GPU (default 2^28, the BASELINE.json size)')
+    ap.add_argument('--configs', action='store_true', help='also time the other BASELINE.json configurations (1 GPU)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,30 @@
+"""Run ONE hot-path kernel a few times at benchmark size (target for ncu). Usage: profile_kernel.py <which> [launches]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from numga_b200 import B200Context
+from bench import device_mv
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'sandwich'
+launches = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+if which == 'sandwich':
+    ctx = B200Context((3, 0, 1)); S = ctx.subspace
+    R = ctx.multivector.motor(np.random.default_rng(1).standard_normal(8).astype(np.float32))
+    p = device_mv(ctx, S.antivector(), 1 << 28, 2, 0)
+    f = ctx.jit(lambda r, x: r >> x); run = lambda: f(R, p)
+elif which == 'gp':
+    ctx = B200Context((3, 0, 1)); S = ctx.subspace
+    a, b = device_mv(ctx, S.even_grade(), 1 << 26, 3, 0), device_mv(ctx, S.even_grade(), 1 << 26, 4, 0)
+    run = lambda: a * b
+elif which == 'cga':
+    ctx = B200Context((4, 1, 0)); F = ctx.subspace.full()
+    a, b = device_mv(ctx, F, 1 << 24, 5, 0), device_mv(ctx, F, 1 << 24, 6, 0)
+    run = lambda: a * b
+elif which in ('roundtrip', 'roundtrip64'):
+    ctx = B200Context((3, 0, 1), dtype=torch.float64 if which.endswith('64') else torch.float32)
+    bv = device_mv(ctx, ctx.subspace.bivector(), 1 << 24, 7, 0, scale=0.5)
+    f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv)
+for _ in range(launches):
+    out = run()
+torch.cuda.synchronize()
+print('ok', which, launches, tuple(out.values.shape))

@@ -136,7 +136,8 @@ def test_operator_call_path_uses_term_table_kernels():
     # broadcast motor through the operator path (bcast_mask), fast mode pre-contraction
     fctx = _ctx((3, 0, 1), np.float32, 'fast')
     R1 = fctx.multivector.motor(a[0])
-    got = fctx.operator.sandwich(S.even_grade(), S.antivector())(R1, fctx.multivector.antivector(p), R1)
+    FS = fctx.subspace
+    got = fctx.operator.sandwich(FS.even_grade(), FS.antivector())(R1, fctx.multivector.antivector(p), R1)
     want = octx.multivector('even_grade', a[0]) >> octx.multivector('antivector', p)
     assert _rel_err(got.numpy(), want.values) < 1e-5
 
