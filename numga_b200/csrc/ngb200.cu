@@ -276,6 +276,99 @@ struct Gen {
         return "T(0)";
     }
 
+    // ---- packed fp32 pairs: value v of items (2k, 2k+1) lives in one float2 -----------------------------------
+    // Scalar FFMA issues at half rate on sm_100 (one warp instruction per 2 cycles per SM sub-partition); the
+    // packed FFMA2 / FMUL2 / FADD2 instructions do two FMAs per lane per issue slot and are the only way to reach
+    // the FP32 peak. Compute-bound programs (exp/log chains, CGA products) therefore run two batch items per
+    // float2 value. nvcc contracts a*b+c only for plain operators, so FAST programs get their FMAs from the
+    // contraction pass below; FAITHFUL programs keep separately rounded __fmul2_rn / __fadd2_rn.
+    std::vector<int> fused_into;   // MUL v is absorbed into the FMA emitted for ADD/SUB fused_into[v]
+    std::vector<int> fuse_mul;     // for ADD/SUB v: which operand (the MUL) it absorbs, or -1
+
+    void plan_contraction() {
+        const int n = (int)P.instr.size();
+        fused_into.assign(n, -1);
+        fuse_mul.assign(n, -1);
+        if (faithful) return;
+        std::vector<int> uses(n, 0);
+        for (int v = 0; v < n; ++v) {
+            if (!live[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            const int ops[3] = {I.a, I.b, I.c};
+            for (int j = 0; j < n_operands_of(I.op); ++j) uses[ops[j]]++;
+        }
+        for (const ngb200_store &st : P.stores) uses[st.value]++;
+        for (int v = 0; v < n; ++v) {
+            if (!live[v] || uniform[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            if (I.op != NGB200_OP_ADD && I.op != NGB200_OP_SUB) continue;
+            const int cand[2] = {I.b, I.a};
+            for (int m : cand) {
+                const ngb200_instr &M = P.instr[m];
+                if (M.op == NGB200_OP_MUL && !uniform[m] && uses[m] == 1 && fused_into[m] < 0 && I.a != I.b) {
+                    fused_into[m] = v;
+                    fuse_mul[v] = m;
+                    break;
+                }
+            }
+        }
+    }
+
+    std::string ref2(int v) const {
+        const ngb200_instr &I = P.instr[v];
+        if (I.op == NGB200_OP_CONST) return "ngb_dup(" + literal(P.consts[I.a], P.dtype) + ")";
+        if (uniform[v]) return "ngb_dup(u[" + std::to_string(uslot[v]) + "])";
+        if (I.op == NGB200_OP_INPUT) return "x[" + std::to_string(xoff[I.a] + I.b) + "]";
+        return "r" + std::to_string(v);
+    }
+
+    std::string expr2(int v) const {
+        const ngb200_instr &I = P.instr[v];
+        const int k = n_operands_of(I.op);
+        std::string a = k >= 1 ? ref2(I.a) : "", b = k >= 2 ? ref2(I.b) : "", c = k >= 3 ? ref2(I.c) : "";
+        auto half = [&](const std::string &fn, const std::string &h) {   // scalar op on one half
+            std::string r = fn;
+            size_t pos;
+            while ((pos = r.find("$a")) != std::string::npos) r.replace(pos, 2, a + "." + h);
+            while ((pos = r.find("$b")) != std::string::npos) r.replace(pos, 2, b + "." + h);
+            while ((pos = r.find("$c")) != std::string::npos) r.replace(pos, 2, c + "." + h);
+            return r;
+        };
+        auto both = [&](const std::string &fn) { return "make_float2(" + half(fn, "x") + ", " + half(fn, "y") + ")"; };
+        switch (I.op) {
+            case NGB200_OP_ADD:
+            case NGB200_OP_SUB: {
+                const bool sub = I.op == NGB200_OP_SUB;
+                int m = fuse_mul[v];
+                if (m >= 0) {
+                    const ngb200_instr &M = P.instr[m];
+                    std::string ma = ref2(M.a), mb = ref2(M.b);
+                    if (m == I.b)   // a +- (ma*mb)
+                        return "__ffma2_rn(" + (sub ? "ngb_neg2(" + ma + ")" : ma) + ", " + mb + ", " + a + ")";
+                    return "__ffma2_rn(" + ma + ", " + mb + ", " + (sub ? "ngb_neg2(" + b + ")" : b) + ")";   // (ma*mb) +- b
+                }
+                return "__fadd2_rn(" + a + ", " + (sub ? "ngb_neg2(" + b + ")" : b) + ")";
+            }
+            case NGB200_OP_MUL: return "__fmul2_rn(" + a + ", " + b + ")";
+            case NGB200_OP_FMA: return "__ffma2_rn(" + a + ", " + b + ", " + c + ")";
+            case NGB200_OP_NEG: return "ngb_neg2(" + a + ")";
+            case NGB200_OP_DIV: return both(faithful ? "__fdiv_rn($a, $b)" : "$a / $b");
+            case NGB200_OP_SQRT: return both(faithful ? "__fsqrt_rn($a)" : "sqrtf($a)");
+            case NGB200_OP_RSQRT: return both(faithful ? "__fdiv_rn(1.0f, __fsqrt_rn($a))" : "1.0f / sqrtf($a)");
+            case NGB200_OP_RCP: return both(faithful ? "__fdiv_rn(1.0f, $a)" : "1.0f / $a");
+            case NGB200_OP_ABS: return both("fabsf($a)");
+            case NGB200_OP_NAN_TO_NUM: return both("ngb_nan_to_num($a, $b)");
+            case NGB200_OP_EXP: return both("expf($a)");
+            case NGB200_OP_LOG: return both("logf($a)");
+            case NGB200_OP_SIN: return both("sinf($a)");
+            case NGB200_OP_COS: return both("cosf($a)");
+            case NGB200_OP_MIN: return both("fminf($a, $b)");
+            case NGB200_OP_MAX: return both("fmaxf($a, $b)");
+            case NGB200_OP_SELECT_GT0: return both("($a > 0.0f ? $b : $c)");
+        }
+        return "ngb_dup(0.0f)";
+    }
+
     int analyse() {
         const int n = (int)P.instr.size();
         live.assign(n, 0);
@@ -341,14 +434,16 @@ struct Gen {
         return NGB200_OK;
     }
 
-    std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform) {
+    std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform, bool pair) {
+        if (pair) plan_contraction();
         const int n = (int)P.instr.size();
         const int nin = (int)P.in_width.size(), nout = (int)P.out_width.size();
         const char *T = f64 ? "double" : "float";
         const char *VT = f64 ? "double2" : (vec == 2 ? "float2" : "float4");
         static const char *lane[4] = {"x", "y", "z", "w"};
         std::string s;
-        appendf(s, "// numga_b200 generated kernel (dtype %s, %s, vec %d)\n", T, faithful ? "faithful" : "fast", vec);
+        appendf(s, "// numga_b200 generated kernel (dtype %s, %s, vec %d%s)\n", T, faithful ? "faithful" : "fast", vec,
+                pair ? ", packed f32x2" : "");
         appendf(s, "typedef %s T;\ntypedef %s VT;\n", T, VT);
         appendf(s, "#define NGB_V %d\n#define NGB_TPB %d\n", vec, P.tpb);
         s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
@@ -401,6 +496,24 @@ struct Gen {
         *n_live = nl;
         *n_uniform = nu;
 
+        // ---- per-PAIR body (fp32): the same program on float2 values, FFMA2 / FMUL2 / FADD2 ----------------------
+        if (pair) {
+            s += "__device__ __forceinline__ float2 ngb_dup(float a) { return make_float2(a, a); }\n";
+            s += "__device__ __forceinline__ float2 ngb_neg2(float2 a) { return make_float2(-a.x, -a.y); }\n";
+            appendf(s, "__device__ __forceinline__ void ngb_body2(const float2 (&x)[%d], const T (&u)[%d], float2 (&y)[%d]) {\n",
+                    NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
+            for (int v = 0; v < n; ++v) {
+                if (!live[v] || uniform[v] || fused_into[v] >= 0) continue;
+                if (P.instr[v].op == NGB200_OP_INPUT) continue;
+                appendf(s, "  const float2 r%d = %s;\n", v, expr2(v).c_str());
+            }
+            for (int j = 0; j < NY; ++j) {
+                if (stored[j] >= 0) appendf(s, "  y[%d] = %s;\n", j, ref2(stored[j]).c_str());
+                else appendf(s, "  y[%d] = ngb_dup(0.0f);\n", j);
+            }
+            s += "}\n";
+        }
+
         // ---- scalar kernel: any strides, gather/scatter -----------------------------------
         appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_scalar(const Params p) {\n");
         appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
@@ -428,7 +541,33 @@ struct Gen {
         s += "  }\n}\n";
 
         // ---- vector kernel: batch_stride 1, 128-bit accesses --------------------------------
-        if (vec > 1) {
+        if (vec > 1 && pair) {
+            // items (0,1) and (2,3) of each thread's vector are processed as float2 pairs
+            const int npair = vec / 2;
+            appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_vec(const Params p) {\n");
+            appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+            s += "  const long long nvec = p.n / NGB_V;\n";
+            s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
+            s += "  for (long long v = (long long)blockIdx.x * NGB_TPB + threadIdx.x; v < nvec; v += stride) {\n";
+            appendf(s, "    float2 x[%d][%d]; float2 y[%d][%d];\n", npair, NX > 0 ? NX : 1, npair, NY > 0 ? NY : 1);
+            for (int k = 0; k < nin; ++k) {
+                if (P.in_mode[k] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < P.in_width[k]; ++c) {
+                    appendf(s, "    { const VT t = NGB_LD(reinterpret_cast<const VT*>(p.in[%d].ptr + %dLL * p.in[%d].cs) + v);", k, c, k);
+                    if (vec == 2) appendf(s, " x[0][%d] = t;", xoff[k] + c);
+                    else appendf(s, " x[0][%d] = make_float2(t.x, t.y); x[1][%d] = make_float2(t.z, t.w);", xoff[k] + c, xoff[k] + c);
+                    s += " }\n";
+                }
+            }
+            appendf(s, "    #pragma unroll\n    for (int l = 0; l < %d; ++l) ngb_body2(x[l], u, y[l]);\n", npair);
+            for (int k = 0; k < nout; ++k)
+                for (int c = 0; c < P.out_width[k]; ++c) {
+                    if (vec == 2) appendf(s, "    { const VT t = y[0][%d];", yoff[k] + c);
+                    else appendf(s, "    { const VT t = make_float4(y[0][%d].x, y[0][%d].y, y[1][%d].x, y[1][%d].y);", yoff[k] + c, yoff[k] + c, yoff[k] + c, yoff[k] + c);
+                    appendf(s, " NGB_ST(reinterpret_cast<VT*>(p.out[%d].ptr + %dLL * p.out[%d].cs) + v, t); }\n", k, c, k);
+                }
+            s += "  }\n}\n";
+        } else if (vec > 1) {
             appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_vec(const Params p) {\n");
             appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
             s += "  const long long nvec = p.n / NGB_V;\n";
@@ -556,14 +695,20 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     if (rc) return rc;
     int live_guess = 0;
     for (char c : gen.live) live_guess += c;
-    int vmax = P->dtype == NGB200_F64 ? 2 : 4;
-    int vec = vec_hint > 0 ? vec_hint : (live_guess <= env_int("NGB200_VEC_INSTR_LIMIT", 700) ? vmax : 1);
+    // items per thread: small programs are HBM-bound -> 128-bit accesses (4 x f32 / 2 x f64); big ones are
+    // compute-bound -> fp32 keeps 2 items (one packed f32x2 pair, 64-bit accesses), fp64 1 item
+    const bool f32 = P->dtype == NGB200_F32;
+    const bool small = live_guess <= env_int("NGB200_VEC_INSTR_LIMIT", 700);
+    int vmax = f32 ? 4 : 2;
+    int vec = vec_hint > 0 ? vec_hint : (small ? vmax : (f32 ? 2 : 1));
+    if (env_int("NGB200_FORCE_VEC", 0) > 0) vec = env_int("NGB200_FORCE_VEC", 0);
     if (vec > vmax) vec = vmax;
     if (vec == 3) vec = 2;
     if (P->any_indexed || gen.NX == 0) vec = 1;
+    const bool pair = f32 && vec >= 2 && env_int("NGB200_PAIR", 1);
     P->vec = vec;
     P->tpb = env_int("NGB200_TPB", 256);
-    P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform);
+    P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform, pair);
     P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
     if (P->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel (%zu parameter bytes)", P->param_bytes);

@@ -24,6 +24,21 @@ elif which in ('roundtrip', 'roundtrip64'):
     ctx = B200Context((3, 0, 1), dtype=torch.float64 if which.endswith('64') else torch.float32)
     bv = device_mv(ctx, ctx.subspace.bivector(), 1 << 24, 7, 0, scale=0.5)
     f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv)
+if which in ('cga_time', 'roundtrip_time'):
+    import time
+    from bench import time_steps
+    if which == 'cga_time':
+        ctx = B200Context((4, 1, 0)); F = ctx.subspace.full(); n = 1 << 26
+        a, b = device_mv(ctx, F, n, 5, 0), device_mv(ctx, F, n, 6, 0)
+        run = lambda: a * b; bpi = 384
+    else:
+        ctx = B200Context((3, 0, 1)); n = 1 << 27
+        bv = device_mv(ctx, ctx.subspace.bivector(), n, 7, 0, scale=0.5)
+        f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv); bpi = 48
+    ms = time_steps(run, 10, 3)
+    prog = list(ctx.engine.cache.values())[-1].program
+    print(which, {k: v for k, v in os.environ.items() if k.startswith('NGB200') and 'CACHE' not in k}, f'{ms:.3f} ms {n/ms/1e6:.2f} G/s {bpi*n/ms/1e6:.0f} GB/s', prog.info['regs_vec'], prog.info['regs_scalar'], prog.info['vec'])
+    sys.exit(0)
 for _ in range(launches):
     out = run()
 torch.cuda.synchronize()
