@@ -251,10 +251,21 @@ struct Gen {
         std::string c = n_operands_of(I.op) >= 3 ? ref(I.c, in_body) : "";
         const char *sfx = f64 ? "" : "f";
         auto rn = [&](const char *op) { return std::string(f64 ? "__d" : "__f") + op + "_rn"; };
+        // Every add / multiply is an explicitly rounded intrinsic and every FMA is one this generator chose
+        // (plan_contraction), so the scalar and the packed kernels of a program compute bit-identical results
+        // and nothing depends on the compiler's contraction heuristics.
+        if (in_body && (I.op == NGB200_OP_ADD || I.op == NGB200_OP_SUB) && !fuse_mul.empty() && fuse_mul[v] >= 0) {
+            const bool sub = I.op == NGB200_OP_SUB;
+            const int m = fuse_mul[v];
+            std::string ma = ref(P.instr[m].a, true), mb = ref(P.instr[m].b, true);
+            std::string f = std::string("fma") + sfx;
+            if (m == I.b) return f + "(" + (sub ? "-" + ma : ma) + ", " + mb + ", " + a + ")";
+            return f + "(" + ma + ", " + mb + ", " + (sub ? "-" + b : b) + ")";
+        }
         switch (I.op) {
-            case NGB200_OP_ADD: return faithful ? rn("add") + "(" + a + ", " + b + ")" : a + " + " + b;
-            case NGB200_OP_SUB: return faithful ? rn("sub") + "(" + a + ", " + b + ")" : a + " - " + b;
-            case NGB200_OP_MUL: return faithful ? rn("mul") + "(" + a + ", " + b + ")" : a + " * " + b;
+            case NGB200_OP_ADD: return rn("add") + "(" + a + ", " + b + ")";
+            case NGB200_OP_SUB: return rn("sub") + "(" + a + ", " + b + ")";
+            case NGB200_OP_MUL: return rn("mul") + "(" + a + ", " + b + ")";
             case NGB200_OP_DIV: return faithful ? rn("div") + "(" + a + ", " + b + ")" : a + " / " + b;
             case NGB200_OP_NEG: return "-" + a;
             case NGB200_OP_SQRT: return faithful ? rn("sqrt") + "(" + a + ")" : std::string("sqrt") + sfx + "(" + a + ")";
@@ -435,7 +446,7 @@ struct Gen {
     }
 
     std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform, bool pair) {
-        if (pair) plan_contraction();
+        plan_contraction();
         const int n = (int)P.instr.size();
         const int nin = (int)P.in_width.size(), nout = (int)P.out_width.size();
         const char *T = f64 ? "double" : "float";
@@ -484,6 +495,7 @@ struct Gen {
             const ngb200_instr &I = P.instr[v];
             if (I.op == NGB200_OP_INPUT) continue;
             ++nl;
+            if (fused_into[v] >= 0) continue;      // this multiply lives inside the FMA of its consumer
             appendf(s, "  const T r%d = %s;\n", v, expr(v, true).c_str());
         }
         std::vector<int> stored(NY > 0 ? NY : 1, -1);
@@ -700,7 +712,10 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     const bool f32 = P->dtype == NGB200_F32;
     const bool small = live_guess <= env_int("NGB200_VEC_INSTR_LIMIT", 700);
     int vmax = f32 ? 4 : 2;
-    int vec = vec_hint > 0 ? vec_hint : (small ? vmax : (f32 ? 2 : 1));
+    // measured on B200 (profiles/): long dependent chains (exp/log: ~110 instructions per operand component) are
+    // fastest with 1 item per thread; wide products (CGA full x full: ~21) gain 10% from 2 items per thread
+    const bool wide = live_guess <= 48 * (gen.NX + gen.NY);
+    int vec = vec_hint > 0 ? vec_hint : (small ? vmax : (f32 && wide ? 2 : 1));
     if (env_int("NGB200_FORCE_VEC", 0) > 0) vec = env_int("NGB200_FORCE_VEC", 0);
     if (vec > vmax) vec = vmax;
     if (vec == 3) vec = 2;

@@ -388,3 +388,65 @@ def _row_fast(trace, terms):
         term = inner if pivot is None else trace.mul(inner, pivot)
         acc = term if acc is None else trace.add(acc, term)
     return acc
+
+
+def lower_partial(trace: Trace, operator, bound, free, kshape):
+    """Kernel of `operator` with inputs `bound` ({axis: value ids}) substituted: for every remaining
+    (free input indices..., output) entry, sum coeff * prod(bound factors).  Returns the flattened kernel
+    (C order over kshape); entries without terms are the constant 0."""
+    arity = operator.arity
+    groups = {}
+    for idx, c in zip(operator.index.tolist(), operator.coeff.tolist()):
+        key = tuple(idx[k] for k in free) + (idx[arity],)
+        groups.setdefault(key, []).append((c, [bound[k][idx[k]] for k in sorted(bound)]))
+    zero = trace.const(0.0)
+    size = 1
+    for n in kshape:
+        size *= n
+    flat = [zero] * size
+    for key, terms in groups.items():
+        pos = 0
+        for k, n in zip(key, kshape):
+            pos = pos * n + k
+        if trace.faithful:
+            acc = None
+            for c, factors in terms:
+                prod = None
+                for f in reversed(factors):
+                    prod = f if prod is None else trace.mul(f, prod)
+                if abs(c) != 1:
+                    prod = trace.mul(prod, trace.const(abs(c)))
+                if acc is None:
+                    acc = prod if c > 0 else trace.neg(prod)
+                else:
+                    acc = trace.add(acc, prod) if c > 0 else trace.sub(acc, prod)
+            flat[pos] = acc
+        else:
+            flat[pos] = _row_fast(trace, terms)
+    return flat
+
+
+def lower_dense(trace: Trace, kernel, kshape, mask, inputs):
+    """out[o] = sum over input index tuples of kernel[j.., o] * prod(inputs[k][j_k]); only entries whose
+    `mask` is set are visited.  `kernel` is the flattened (C order) list of value ids."""
+    import itertools
+    n_out = kshape[-1]
+    zero = None
+    out = []
+    for o in range(n_out):
+        acc = None
+        for js in itertools.product(*[range(n) for n in kshape[:-1]]):
+            if not mask[js + (o,)]:
+                continue
+            pos = 0
+            for k, n in zip(js + (o,), kshape):
+                pos = pos * n + k
+            prod = kernel[pos]
+            for k, j in enumerate(js):
+                prod = trace.mul(prod, inputs[k][j])
+            acc = prod if acc is None else trace.add(acc, prod)
+        if acc is None:
+            zero = trace.const(0.0) if zero is None else zero
+            acc = zero
+        out.append(acc)
+    return out
