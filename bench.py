@@ -245,7 +245,55 @@ def other_configs(torch, B200Context, rank, peak):
     x, y = device_mv(cga, F, n, 14, rank), device_mv(cga, F, n, 15, rank)
     ms = time_steps(lambda: x * y, 10, 3)
     entry('config 4: CGA (4,1,0) full*full geometric product, batch 2^26 (SIMT, 1024 FMA/item)', 384, n, ms, flops=2016)
+    del x, y
+    for dtype, tag in ((torch.float32, 'fp32'), (torch.float64, 'fp64')):
+        out.append(physics_config(torch, B200Context, rank, peak, dtype, tag))
     return out
+
+
+def physics_config(torch, B200Context, rank, peak, dtype, tag, n_target=1 << 24):
+    """BASELINE.json configs[4]: the rigid-body core step (numga/examples/physics/core.py Body.integrate with two
+    constraint colour sets) on ~2^24 bodies = independent 12-body chains, as SIX fused kernels per sub-step."""
+    from numga_b200 import runtime as rt
+    from numga_b200.examples.physics import FusedStep, replicate_chains, setup_bodies
+    c = B200Context('x+y+z+w0', dtype=dtype)
+    bodies, sets = setup_bodies(c, n_bodies=12)
+    n_chains = n_target // 12
+    big, bsets = replicate_chains(bodies, sets, n_chains)
+    n_bodies = 12 * n_chains
+    n_constraints = sum(int(s.body_idx.shape[1]) for s in bsets)
+    big = big.copy(rate=big.rate + device_mv(c, c.subspace.bivector(), n_bodies, 16, rank, scale=0.3))
+    fs = FusedStep(big, bsets)
+    state = [big]
+
+    def step():
+        state[0] = fs.integrate(state[0], 1 / 200)
+    l0 = rt.launch_count()
+    step()
+    launches = rt.launch_count() - l0
+    ms = time_steps(step, 10, 3)
+    finite = bool(torch.isfinite(state[0].motor.values).all().item() and torch.isfinite(state[0].rate.values).all().item())
+    # compulsory traffic of the six-kernel split: live input components + outputs (+ gather indices) per item
+    es = 4 if dtype == torch.float32 else 8
+    words, instr = {}, {}
+    for k, v in c.engine.cache.items():
+        if k[0][0] != 'jit':
+            continue
+        name = k[0][1].__name__
+        live_in = sum(1 for op, a, b, _ in v.ir['instr'] if op == rt.OP_INPUT and v.program.in_mode[a] != rt.BROADCAST)
+        words[name] = live_in + sum(v.ir['out_width'])
+        instr[name] = v.program.info['n_instr']
+    per_body = (words['pre'] + words['post']) * es
+    per_constraint = (words['apply'] + words['v_apply']) * es + 2 * 2 * 8      # two int64 body indices, two kernels
+    total = per_body * n_bodies + per_constraint * n_constraints
+    flops = (instr['pre'] + instr['post']) * n_bodies + (instr['apply'] + instr['v_apply']) * n_constraints
+    gbs = total / ms / 1e6
+    return {'config': f'config 5: rigid-body XPBD sub-step (Body.integrate, 2 colour sets), {tag}, {n_bodies} bodies in {n_chains} chains, '
+                      f'{launches} fused kernels per sub-step', 'items': n_bodies, 'ms': ms, 'items_per_s': n_bodies / ms * 1e3,
+            'bytes_per_item': total / n_bodies, 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak,
+            'tflops': flops / ms / 1e9, 'kernel_launches_per_step': launches, 'state_finite': finite,
+            'note': 'bytes = live inputs + outputs of the six kernels (pre, apply x2, post, v_apply x2) incl. gathered inertia '
+                    'matrices; the state-once minimum of SURVEY.md 8d (728 B fp32) would need a single pass'}
 
 
 def run_ours(args):

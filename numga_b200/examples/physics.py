@@ -1,0 +1,287 @@
+"""XPBD rigid-body chain in geometric algebra — the core step of numga's physics example, on the B200 backend.
+
+Mirrors `numga/examples/physics/{core,base,setup_chain}.py` and `examples/integrators.py` (same class and method
+names, same formulas: Verlet-style integrate = pre_integrate (RK4 on Euler's equation) -> constraint relaxation
+per colour set -> post_integrate -> velocity relaxation per colour set).  Two ways to run a step:
+
+  * `Body.integrate(dt, constraint_sets)`        generic path, written like the reference on `[2, c]`-shaped
+    multivectors; every multivector method is one generated kernel (174 reference array passes -> ~120 kernels);
+  * `FusedStep(bodies, constraint_sets).integrate(bodies, dt)`   the B200 path: SIX kernels per sub-step for two
+    colour sets — pre-integrate, constraint-apply x2, post-integrate, velocity-apply x2 — each traced from the
+    same method bodies below with `context.jit`.  The constraint kernels GATHER the two bodies of every constraint
+    through an index operand and SCATTER the updated motors / rates back in place (each body is touched at most
+    once per colour set, numga/examples/physics/setup_chain.py:66-67, so the scatter is race-free).
+"""
+import numpy as np
+
+from numga_b200.backend import B200DenseOperator
+
+
+def RK4(f, y, h):
+    """Classic Runge-Kutta step (examples/integrators.py:7-12)."""
+    k1 = f(y)
+    k2 = f(y + 0.5 * h * k1)
+    k3 = f(y + 0.5 * h * k2)
+    k4 = f(y + h * k3)
+    return y + (h / 3) * (k2 + k3 + (k1 + k4) * 0.5)
+
+
+def motor_add_step(motor, step):
+    """Apply an integrated-rate bivector to a motor; linearised exp (core.py:33-35)."""
+    return motor * (step * (-1 / 2)).exp_linear_normalized()
+
+
+def motor_relative_step(old, new):
+    """Bivector step between two motor states (core.py:36-38)."""
+    return new.reverse_product(old).motor_log_linear_normalized() * -(2)
+
+
+class Body:
+    """A set of rigid bodies (leading batch axis).  motor: body->world; rate: bivector, body frame;
+    first_moment: sum of mass points; inertia / inertia_inv: bound unary operators (rates <-> momentum lines)."""
+
+    def __init__(self, motor, rate, first_moment, inertia, inertia_inv, damping, gravity):
+        assert motor.subspace.equals.motor()
+        assert rate.subspace.equals.bivector()
+        assert gravity.subspace.inside.antivector()
+        assert inertia.output.equals.antibivector()
+        assert inertia_inv.output.equals.bivector()
+        assert damping.subspace.equals.scalar()
+        self.motor, self.rate, self.first_moment = motor, rate, first_moment
+        self.inertia, self.inertia_inv, self.damping, self.gravity = inertia, inertia_inv, damping, gravity
+
+    _FIELDS = ('motor', 'rate', 'first_moment', 'inertia', 'inertia_inv', 'damping', 'gravity')
+
+    def __getitem__(self, idx):
+        return type(self)(*(getattr(self, f)[idx] for f in self._FIELDS))
+
+    def concatenate(self, other):
+        return type(self)(*(getattr(self, f).concatenate(getattr(other, f), axis=0) for f in self._FIELDS))
+
+    def copy(self, motor=None, rate=None, gravity=None, damping=None):
+        return type(self)(
+            motor=self.motor if motor is None else motor, rate=self.rate if rate is None else rate,
+            damping=self.damping if damping is None else damping, gravity=self.gravity if gravity is None else gravity,
+            first_moment=self.first_moment, inertia=self.inertia, inertia_inv=self.inertia_inv)
+
+    @classmethod
+    def from_point_cloud(cls, points):
+        """Body from mass points [..., n_points] (base.py:92-124): first moment = sum of points, inertia map =
+        sum of the per-point maps  rate -> point & (point x rate)."""
+        context = points.context
+        assert points.subspace.inside.antivector()
+        first_moment = points.sum(axis=-2)
+        inertia = points.inertia_map().sum(axis=-3)
+        ones = np.ones(first_moment.shape)
+        return cls(
+            motor=context.multivector.motor() * ones, rate=context.multivector.bivector() * ones,
+            first_moment=first_moment, inertia=inertia, inertia_inv=inertia.inverse(),
+            damping=context.multivector.scalar() * ones * 0, gravity=context.multivector.antivector() * ones)
+
+    def kinetic_energy(self):
+        return self.inertia(self.rate) & self.rate
+
+    # ---- dynamics (core.py:41-88) -------------------------------------------------------------------------
+    def forques(self):
+        """External forque line per body, body frame: linear damping + gravity acting on the first moment."""
+        damping = -(self.rate * self.damping).dual()
+        gravity = self.first_moment & (self.motor << self.gravity)
+        return damping + gravity
+
+    def rate_derivative(self):
+        """Euler's equation: d/dt rate = I^-1 (forque - I(rate) x rate)."""
+        return self.inertia_inv(self.forques() - self.inertia(self.rate).commutator(self.rate))
+
+    def pre_integrate(self, dt):
+        rate = RK4(lambda r: self.copy(rate=r).rate_derivative(), self.rate, dt)
+        return self.copy(motor=motor_add_step(self.motor, rate * dt), rate=rate)
+
+    def post_integrate(self, old, dt):
+        motor = self.motor.normalized()
+        rate = motor_relative_step(motor.reverse(), old.motor.reverse()) / dt
+        return self.copy(rate=rate, motor=motor)
+
+    def integrate(self, dt, constraint_sets=()):
+        new = self.pre_integrate(dt)
+        for c in constraint_sets:
+            new = c.apply(new, dt=dt)
+        new = new.post_integrate(self, dt=dt)
+        for c in constraint_sets:
+            new = c.v_apply(new, dt=dt)
+        return new
+
+
+class Constraint:
+    """Point-to-point constraints: anchors [2, n] are the body-local attachment points of bodies body_idx [2, n]."""
+
+    def __init__(self, body_idx, anchors, compliance):
+        context = anchors.context
+        assert anchors.subspace.equals.antivector()
+        assert compliance.subspace.equals.scalar()
+        self.body_idx = context.coerce_array(body_idx, dtype=int)
+        self.anchors = anchors
+        self.anchors_map = anchors.inertia_map()          # rates -> velocity line at the anchor
+        self.compliance = compliance
+        self.connectivity = context.multivector.scalar([[+1 / 2], [-1 / 2]])[:, None]   # +-1/2 per side, shape (2, 1)
+        assert self.connectivity.shape == (2, 1)
+
+    def __getitem__(self, idx):
+        return type(self)(self.body_idx[:, idx], self.anchors[:, idx], self.compliance[idx])
+
+    def concatenate(self, other):
+        import torch
+        return type(self)(torch.cat([self.body_idx, other.body_idx], dim=1),
+                          self.anchors.concatenate(other.anchors, axis=1),
+                          self.compliance.concatenate(other.compliance, axis=0))
+
+    def apply(self, bodies, dt):
+        idx = self.body_idx
+        motors = self.apply_indexed(bodies.motor[idx], bodies.inertia_inv[idx], dt)
+        return bodies.copy(motor=bodies.motor.at[idx].set(motors))
+
+    def apply_indexed(self, motors, inertia_inv, dt):
+        """Move both bodies so that the anchors meet, balancing constraint work and inertial work (core.py:104-120)."""
+        anchors = motors >> self.anchors                     # [2, c] anchors in world space
+        forque = anchors[0] & anchors[1]                     # [c] connecting line
+        magnitude = forque.norm()                            # [c] violation
+        direction = forque / (magnitude + 1e-26)
+        steps = self.distribute_forque(motors << direction, magnitude, inertia_inv, self.compliance / dt ** 2)
+        return motor_add_step(motors, steps)
+
+    def v_apply(self, bodies, dt):
+        idx = self.body_idx
+        rates = self.v_apply_indexed(bodies.motor[idx], bodies.rate[idx], bodies.inertia_inv[idx], dt)
+        return bodies.copy(rate=bodies.rate.at[idx].set(rates))
+
+    def v_apply_indexed(self, motors, rates, inertia_inv, dt):
+        """Exchange a velocity impulse along the constraint (core.py:129-146)."""
+        velocities = motors >> self.anchors_map(rates)       # [2, c] world-space velocity lines
+        forque = -(self.connectivity * velocities).sum(axis=0)
+        magnitude = forque.norm()
+        direction = forque / (magnitude + 1e-26)
+        steps = self.distribute_forque(motors << direction, magnitude, inertia_inv, self.compliance * 0)
+        return rates + steps
+
+    def distribute_forque(self, directions, magnitude, inertias_inv, constraint_compliance):
+        """Split an impulse along `directions` [2, c] into momentum-conserving bivector steps (core.py:148-167)."""
+        steps = inertias_inv(directions)
+        inertial_compliances = steps & directions
+        total_compliance = constraint_compliance + inertial_compliances.sum(axis=0)
+        multiplier = magnitude / total_compliance
+        return steps * self.connectivity * multiplier
+
+
+def setup_bodies(context, fixing=True, n_bodies=12, compliance=1e-9, distance=9e-2, size=5e-2, damping=1e-3):
+    """A chain of identical bodies linked by point constraints, first body pinned (setup_chain.py:8-67).
+    Returns (bodies, [red constraints, black constraints])."""
+    *axes, origin = context.multivector.basis()            # last basis vector = origin / projective direction
+    model_space = axes[0].subspace
+    for a in axes[1:]:
+        model_space = model_space.union(a.subspace)
+    horizon = origin.subspace.wedge(model_space)           # translation-like bivector directions
+    ndim = len(axes)
+
+    def translator(d):
+        return ((origin / -2) ^ context.multivector(model_space, d)).exp()
+
+    def point_embed(d):
+        return translator(d) >> origin.dual_inverse()
+
+    cube = np.array(np.kron(np.diag(np.arange(ndim) + 1) / ndim, [+1, -1]).T)     # 2*ndim mass points
+    bodies = Body.from_point_cloud(points=point_embed(cube * size))
+    bodies = bodies.copy(gravity=(axes[0] * 5e-2).dual_inverse())
+    bodies = bodies.copy(damping=bodies.damping + damping)
+
+    d = np.arange(n_bodies) * distance
+    qs = translator(np.array([d * 0] * (ndim - 1) + [d]).T)
+    bodies = bodies[None][np.zeros(n_bodies, int)]
+    bodies = bodies.copy(motor=bodies.motor * qs)
+
+    i = np.arange(n_bodies - 1)
+    body_idx = np.array([i, i + 1])
+    a = np.array([[0] * (ndim - 1) + [distance], [0] * (ndim - 1) + [-distance]]) / 2
+    anchors = point_embed(a[:, None, :] * np.ones((1, n_bodies - 1, 1)))
+    ones = context.multivector.scalar(np.ones((n_bodies - 1, 1)))
+    constraints = Constraint(body_idx, anchors, compliance=ones * compliance)
+    if fixing:      # pin body 0: zero the translation-like columns of its inverse inertia
+        idx = bodies.inertia_inv.output.to_relative_indices(horizon.blades)
+        bodies.inertia_inv = bodies.inertia_inv.at[0, :, idx].set(0)
+    return bodies, [constraints[0::2], constraints[1::2]]
+
+
+def replicate_chains(bodies, constraint_sets, n_chains):
+    """n_chains independent copies of a chain laid out chain-major (block-diagonal body_idx): the config-5
+    workload.  Chains never interact, so the batch shards across GPUs by chain with no exchange."""
+    import torch
+    nb = bodies.motor.shape[0]
+    rep = lambda mv: mv[np.tile(np.arange(mv.shape[0]), n_chains)]
+    big = Body(*(rep(getattr(bodies, f)) for f in Body._FIELDS))
+    sets = []
+    for c in constraint_sets:
+        nc = c.body_idx.shape[1]
+        offs = (torch.arange(n_chains, device=c.body_idx.device) * nb).repeat_interleave(nc)
+        sets.append(Constraint(c.body_idx.repeat(1, n_chains) + offs[None, :], c.anchors[:, np.tile(np.arange(nc), n_chains)],
+                               c.compliance[np.tile(np.arange(nc), n_chains)]))
+    return big, sets
+
+
+class FusedStep:
+    """The sub-step as six generated kernels (see module docstring).  State arrays are updated IN PLACE on buffers
+    this object owns, so one `integrate` reads and writes each state component a small fixed number of times."""
+
+    def __init__(self, bodies, constraint_sets):
+        ctx = self.context = bodies.motor.context
+        self.sets = constraint_sets
+        jit = ctx.jit
+
+        def pre(motor, rate, first_moment, inertia, inertia_inv, damping, gravity, dt):
+            b = Body(motor, rate, first_moment, inertia, inertia_inv, damping, gravity)
+            new = b.pre_integrate(dt)
+            return new.motor, new.rate
+        self._pre = jit(pre)
+
+        def post(motor, old_motor, dt):
+            m = motor.normalized()
+            return m, motor_relative_step(m.reverse(), old_motor.reverse()) / dt
+        self._post = jit(post)
+
+        def apply(m0, m1, inv0, inv1, a0, a1, compliance, dt):
+            w0, w1 = m0 >> a0, m1 >> a1
+            forque = w0 & w1
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            s0, s1 = self._distribute(m0 << direction, m1 << direction, magnitude, inv0, inv1, compliance / (dt * dt))
+            return motor_add_step(m0, s0), motor_add_step(m1, s1)
+        self._apply = jit(apply)
+
+        def v_apply(m0, m1, r0, r1, inv0, inv1, map0, map1, compliance, dt):
+            v0, v1 = m0 >> map0(r0), m1 >> map1(r1)
+            forque = -(v0 * 0.5 + v1 * -0.5)
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            s0, s1 = self._distribute(m0 << direction, m1 << direction, magnitude, inv0, inv1, compliance * 0)
+            return r0 + s0, r1 + s1
+        self._v_apply = jit(v_apply)
+
+    @staticmethod
+    def _distribute(d0, d1, magnitude, inv0, inv1, constraint_compliance):
+        s0, s1 = inv0(d0), inv1(d1)
+        total = constraint_compliance + ((s0 & d0) + (s1 & d1))
+        multiplier = magnitude / total
+        return s0 * 0.5 * multiplier, s1 * -0.5 * multiplier
+
+    def integrate(self, bodies, dt):
+        motor, rate = self._pre(bodies.motor, bodies.rate, bodies.first_moment, bodies.inertia, bodies.inertia_inv,
+                                bodies.damping, bodies.gravity, dt)
+        for c in self.sets:
+            i0, i1 = c.body_idx[0], c.body_idx[1]
+            self._apply(motor.indexed(i0), motor.indexed(i1), bodies.inertia_inv.indexed(i0),
+                        bodies.inertia_inv.indexed(i1), c.anchors[0], c.anchors[1], c.compliance, dt,
+                        out=(motor.indexed(i0), motor.indexed(i1)))
+        motor, rate = self._post(motor, bodies.motor, dt)
+        for c in self.sets:
+            i0, i1 = c.body_idx[0], c.body_idx[1]
+            self._v_apply(motor.indexed(i0), motor.indexed(i1), rate.indexed(i0), rate.indexed(i1),
+                          bodies.inertia_inv.indexed(i0), bodies.inertia_inv.indexed(i1), c.anchors_map[0],
+                          c.anchors_map[1], c.compliance, dt, out=(rate.indexed(i0), rate.indexed(i1)))
+        return bodies.copy(motor=motor, rate=rate)

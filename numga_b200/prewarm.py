@@ -69,6 +69,15 @@ def prewarm(batch=8):
                 run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
     for ctx, fn, specs in bench_programs(ctx_of):
         run(ctx, fn, specs)
+    # rigid-body physics (config 5): the generic per-method kernels and the six fused kernels of a sub-step
+    from numga_b200.examples.physics import FusedStep, setup_bodies
+    for dtype in (torch.float32, torch.float64):
+        for mode in ('fast', 'faithful'):
+            ctx = ctx_of('x+y+z+w0', dtype, mode)
+            bodies, sets = setup_bodies(ctx, n_bodies=12)
+            bodies.integrate(1 / 200, sets)
+            FusedStep(bodies, sets).integrate(bodies, 1 / 200)
+            bodies.kinetic_energy()
     after = len(os.listdir(rt_cache_dir())) if os.path.isdir(rt_cache_dir()) else 0
     return max(after, before) // 2
 

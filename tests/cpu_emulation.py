@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE ONLY: run the product's host logic on CPU tensors by replacing kernel launches with the
+numpy IR interpreter (tests/ir_interp.py).
+
+The product (numga_b200/) has no CPU execution path and no hook for one; this module monkeypatches
+`CompiledFunction.__call__` / `B200Operator.__call__` from the outside, inside a context manager, so that the CPU
+test tier can check orchestration logic numerically (broadcasting, gather/scatter, the physics step) against golden
+data without a GPU.  The arithmetic is that of the IR, op by op in the context dtype (= FAITHFUL semantics).
+"""
+import contextlib
+
+import numpy as np
+import torch
+
+from ir_interp import run_ir
+from numga_b200 import backend as B
+from numga_b200 import runtime as rt
+
+
+@contextlib.contextmanager
+def emulate_launches():
+    orig_call, orig_op_call = B.CompiledFunction.__call__, B.B200Operator.__call__
+
+    def compiled_call(self, args, bshape=None, out=None):
+        ctx = self.context
+        mvs = [(role[1], a) for role, a in zip(self.arg_roles, args) if role[0] == 'mv']
+        params = [float(a) for role, a in zip(self.arg_roles, args) if role[0] == 'param']
+        if bshape is None:
+            bshape = B._broadcast([B._batch_shape(a) for _, a in mvs])
+        n_batch = B._prod(bshape)
+        np_dtype = B._NP_DTYPE[ctx.dtype]
+        inputs = [None] * len(mvs)
+        for k, a in mvs:
+            if isinstance(a, B.Indexed):                       # gather
+                inputs[k] = a.as_mv().values.detach().cpu().numpy()[a.index.cpu().numpy()]
+                continue
+            v = a.values.detach().cpu().numpy()
+            if self.program.in_mode[k] == rt.BROADCAST:
+                inputs[k] = v.reshape(-1)
+            else:
+                inputs[k] = np.broadcast_to(v, tuple(bshape) + (v.shape[-1],)).reshape(n_batch, v.shape[-1])
+        outs = run_ir(self.ir, inputs, np_dtype, params) if n_batch else [np.zeros((0, w), np_dtype) for w in self.ir['out_width']]
+        result = []
+        if out is not None:                                    # in-place destinations (scatter for Indexed)
+            for dest, o in zip(out, outs):
+                if isinstance(dest, B.Indexed):
+                    dest.as_mv().values[dest.index] = torch.as_tensor(np.ascontiguousarray(o)).to(ctx.dtype)
+                    result.append(dest.target)
+                else:
+                    dest.values.copy_(torch.as_tensor(np.ascontiguousarray(o)).reshape(dest.values.shape))
+                    result.append(dest)
+            return result[0] if self.single else tuple(result)
+        for s, o in zip(self.out_subspaces, outs):
+            t = B.to_soa(torch.as_tensor(np.ascontiguousarray(o[:max(n_batch, 1)])).reshape(tuple(bshape) + (len(s),))) \
+                if n_batch > 1 else torch.as_tensor(np.ascontiguousarray(o[:n_batch].reshape(tuple(bshape) + (len(s),))))
+            result.append(ctx.mvtype(ctx, s, t.to(ctx.dtype)))
+        return result[0] if self.single else tuple(result)
+
+    def operator_call(self, *inputs):
+        if any(isinstance(i, (B.SubSpace, B.TracedMultiVector)) for i in inputs) or len(self.output) == 0:
+            return orig_op_call(self, *inputs)
+        return self.context.engine.call(('operator', id(self.operator)), lambda *xs: orig_op_call(self, *xs), inputs)
+
+    B.CompiledFunction.__call__, B.B200Operator.__call__ = compiled_call, operator_call
+    try:
+        yield
+    finally:
+        B.CompiledFunction.__call__, B.B200Operator.__call__ = orig_call, orig_op_call
+
+
+def emulated_context(algebra, dtype=torch.float64, mode='faithful'):
+    """A context on CPU tensors for use inside `emulate_launches()`."""
+    return B.B200Context(algebra, dtype=dtype, device='cpu', mode=mode, compile_only=True)

@@ -1,0 +1,131 @@
+"""Rigid-body physics core step (BASELINE.json config 5) against golden states produced by the
+UNMODIFIED reference (`tests/golden/make_golden_physics.py` -> `tests/golden/physics.npz`).
+
+CPU tier: the host orchestration (setup, gather/scatter, colour sets, the six fused kernels' traces) is checked
+numerically by interpreting the traced IR with numpy (tests/cpu_emulation.py; test infrastructure, the product has no
+CPU path).  GPU tier: the same checks with the real kernels through the C ABI.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, 'golden', 'physics.npz'))
+DT = 1 / 200
+TORCH = {'f32': torch.float32, 'f64': torch.float64}
+# position-like state (motors) / velocity-like state (rates: finite differences divided by dt amplify rounding by 1/dt)
+TOL = {'f64': (1e-12, 1e-10), 'f32': (1e-5, 5e-3)}
+
+
+def _err(got, want):
+    return float(np.abs(np.asarray(got) - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def _check_setup(bodies, sets, tag):
+    for f in ('motor', 'rate', 'first_moment', 'damping', 'gravity'):
+        assert _err(getattr(bodies, f).values.cpu().numpy(), G[f'{tag}/init/{f}']) < (1e-6 if tag == 'f32' else 1e-14), f
+    assert bodies.gravity.subspace.blades.astype(np.int64).tolist() == G[f'{tag}/init/gravity_blades'].tolist()
+    assert _err(bodies.inertia.kernel.cpu().numpy(), G[f'{tag}/init/inertia']) < (1e-5 if tag == 'f32' else 1e-13)
+    assert _err(bodies.inertia_inv.kernel.cpu().numpy(), G[f'{tag}/init/inertia_inv']) < (1e-4 if tag == 'f32' else 1e-11)
+    for k, c in enumerate(sets):
+        assert np.array_equal(c.body_idx.cpu().numpy(), G[f'{tag}/set{k}/body_idx'])
+        assert _err(c.anchors.values.cpu().numpy(), G[f'{tag}/set{k}/anchors']) < (1e-6 if tag == 'f32' else 1e-14)
+        assert _err(c.anchors_map.kernel.cpu().numpy(), G[f'{tag}/set{k}/anchors_map']) < (1e-6 if tag == 'f32' else 1e-14)
+        assert _err(c.compliance.values.cpu().numpy(), G[f'{tag}/set{k}/compliance']) < 1e-6
+
+
+def _stages(bodies, sets, tag):
+    """The reference's sub-step, stage by stage, through the generic (one kernel per multivector method) path."""
+    mt, rt_ = TOL[tag]
+    new = bodies.pre_integrate(DT)
+    assert _err(new.motor.values.cpu().numpy(), G[f'{tag}/pre/motor']) < mt
+    assert _err(new.rate.values.cpu().numpy(), G[f'{tag}/pre/rate']) < mt
+    for k, c in enumerate(sets):
+        new = c.apply(new, dt=DT)
+        assert _err(new.motor.values.cpu().numpy(), G[f'{tag}/apply{k}/motor']) < mt
+    new = new.post_integrate(bodies, dt=DT)
+    assert _err(new.motor.values.cpu().numpy(), G[f'{tag}/post/motor']) < mt
+    assert _err(new.rate.values.cpu().numpy(), G[f'{tag}/post/rate']) < rt_
+    for k, c in enumerate(sets):
+        new = c.v_apply(new, dt=DT)
+        assert _err(new.rate.values.cpu().numpy(), G[f'{tag}/vapply{k}/rate']) < rt_
+
+
+def _fused_steps(bodies, sets, tag, steps=(1, 2, 5)):
+    from numga_b200.examples.physics import FusedStep
+    mt, rt_ = TOL[tag]
+    fs = FusedStep(bodies, sets)
+    b = bodies
+    for step in range(1, max(steps) + 1):
+        b = fs.integrate(b, DT)
+        if step in steps:
+            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt * step
+            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_ * step
+    return b
+
+
+def _start(ctx, tag):
+    from numga_b200.examples.physics import setup_bodies
+    bodies, sets = setup_bodies(ctx, n_bodies=12)
+    _check_setup(bodies, sets, tag)
+    return bodies.copy(rate=ctx.multivector.bivector(G[f'{tag}/start/rate'])), sets
+
+
+# ---- CPU tier (numpy interpretation of the traced IR) -------------------------------------------------------------
+def test_physics_generic_and_fused_step_cpu_emulated():
+    from cpu_emulation import emulate_launches, emulated_context
+    from numga_b200.examples.physics import FusedStep, replicate_chains
+    with emulate_launches():
+        ctx = emulated_context('x+y+z+w0', torch.float64)
+        bodies, sets = _start(ctx, 'f64')
+        _stages(bodies, sets, 'f64')
+        _fused_steps(bodies, sets, 'f64', steps=(1, 2))
+        # the fused sub-step is six kernels for two colour sets; constraint kernels gather and scatter in place
+        fs = FusedStep(bodies, sets)
+        fs.integrate(bodies, DT)
+        kinds = sorted({(k[0][1].__name__, v.program.in_mode.count(2), v.program.out_mode.count(2))
+                       for k, v in ctx.engine.cache.items() if k[0][0] == "jit"})
+        assert kinds == [('apply', 4, 2), ('post', 0, 0), ('pre', 0, 0), ('v_apply', 6, 2)]
+        # replicated chains (config 5 workload): block-diagonal constraints, every chain evolves identically
+        big, bsets = replicate_chains(bodies, sets, 3)
+        one = fs.integrate(bodies, DT)
+        many = FusedStep(big, bsets).integrate(big, DT)
+        assert np.array_equal(many.motor.values.numpy().reshape(3, 12, 8), np.broadcast_to(one.motor.values.numpy(), (3, 12, 8)))
+        assert np.array_equal(many.rate.values.numpy().reshape(3, 12, 6), np.broadcast_to(one.rate.values.numpy(), (3, 12, 6)))
+        # the caller's state is never modified (immutable value semantics)
+        assert _err(bodies.rate.values.numpy(), G['f64/start/rate']) == 0
+
+
+# ---- GPU tier ----------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('mode', ['fast', 'faithful'])
+def test_physics_step_gpu_vs_reference(tag, mode):
+    from numga_b200 import B200Context
+    ctx = B200Context('x+y+z+w0', dtype=TORCH[tag], device='cuda:0', mode=mode)
+    bodies, sets = _start(ctx, tag)
+    _stages(bodies, sets, tag)
+    _fused_steps(bodies, sets, tag)
+
+
+@pytest.mark.gpu
+def test_physics_replicated_chains_gpu():
+    """Config-5 workload shape: many independent chains in one batch; each chain must follow the single chain
+    exactly (same kernels, same arithmetic), and the energy stays finite over a few sub-steps."""
+    from numga_b200 import B200Context
+    from numga_b200.examples.physics import FusedStep, replicate_chains
+    ctx = B200Context('x+y+z+w0', dtype=torch.float32, device='cuda:0')
+    bodies, sets = _start(ctx, 'f32')
+    n_chains = 1000
+    big, bsets = replicate_chains(bodies, sets, n_chains)
+    fs1, fsn = FusedStep(bodies, sets), FusedStep(big, bsets)
+    one, many = bodies, big
+    for _ in range(3):
+        one, many = fs1.integrate(one, DT), fsn.integrate(many, DT)
+    m = many.motor.values.cpu().numpy().reshape(n_chains, 12, 8)
+    r = many.rate.values.cpu().numpy().reshape(n_chains, 12, 6)
+    assert np.array_equal(m, np.broadcast_to(one.motor.values.cpu().numpy(), m.shape))
+    assert np.array_equal(r, np.broadcast_to(one.rate.values.cpu().numpy(), r.shape))
+    assert np.isfinite(many.kinetic_energy().values.cpu().numpy()).all()
