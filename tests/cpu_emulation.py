@@ -69,4 +69,6 @@ def emulate_launches():
 
 def emulated_context(algebra, dtype=torch.float64, mode='faithful'):
     """A context on CPU tensors for use inside `emulate_launches()`."""
-    return B.B200Context(algebra, dtype=dtype, device='cpu', mode=mode, compile_only=True)
+    ctx = B.B200Context(algebra, dtype=dtype, device='cpu', mode=mode, compile_only=True)
+    ctx.compile_only = False     # every launch site is patched; host-side torch set-up work (e.g. inverse()) runs for real
+    return ctx
