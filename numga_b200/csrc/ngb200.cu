@@ -68,7 +68,7 @@ extern "C" int64_t ngb200_launch_count(void) { return g_launches.load(); }
     X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData)        \
     X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute)                                \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemAlloc) X(cuMemFree)                     \
-    X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemcpy2DAsync) X(cuStreamCreate)                \
+    X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuStreamCreate)                \
     X(cuStreamSynchronize) X(cuStreamDestroy) X(cuMemAllocHost) X(cuMemFreeHost)
 
 struct Driver {
@@ -164,6 +164,7 @@ struct ngb200_program {
     std::vector<ngb200_store> stores;
     int vec = 1;          // items per thread in the vector kernel (1 = no vector kernel)
     int tpb = 256;
+    int minb = 1;         // __launch_bounds__ min resident CTAs per SM (caps registers at 65536 / (tpb * minb))
     int n_live = 0, n_uniform = 0;
     bool cache_hit = false;
     std::string source, hash;
@@ -172,7 +173,11 @@ struct ngb200_program {
     Loaded loaded[kMaxDevices];
     size_t param_bytes = 0;
     bool any_indexed = false;
+    std::mutex host_mu;
+    struct HostPipe *host = nullptr;   // staging resources of ngb200_program_run_host, created on first use
 };
+
+static void host_pipe_destroy(struct HostPipe *h);
 
 static int esize(int dtype) { return dtype == NGB200_F64 ? 8 : 4; }
 
@@ -220,17 +225,23 @@ static int n_operands_of(int op) {
     }
 }
 
+static int env_int(const char *name, int dflt);
+
 struct Gen {
     const ngb200_program &P;
     bool f64, faithful;
+    bool approx = false;      // FAST fp32: MUFU-based reciprocal / square roots
     std::vector<char> live, uniform;
     std::vector<int> uslot;   // export slot of uniform values used by varying code
     std::vector<int> xoff;    // offset of each varying input in x[]
     std::vector<int> yoff;    // offset of each output in y[]
     int NX = 0, NU = 0, NY = 0;
+    int max_live = 0;         // peak number of simultaneously live per-item values (see analyse)
 
     explicit Gen(const ngb200_program &p)
-        : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {}
+        : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {
+        approx = !f64 && !faithful && !env_int("NGB200_PRECISE_MATH", 0);
+    }
 
     // name of value v as seen from uniform (preamble) or varying (body) code
     std::string ref(int v, bool in_body) const {
@@ -268,11 +279,20 @@ struct Gen {
             case NGB200_OP_MUL: return rn("mul") + "(" + a + ", " + b + ")";
             case NGB200_OP_DIV: return faithful ? rn("div") + "(" + a + ", " + b + ")" : a + " / " + b;
             case NGB200_OP_NEG: return "-" + a;
-            case NGB200_OP_SQRT: return faithful ? rn("sqrt") + "(" + a + ")" : std::string("sqrt") + sfx + "(" + a + ")";
+            // FAST fp32: MUFU approximations (rcp 1 ulp, sqrt / rsqrt ~1-2 ulp, 0 / inf / nan behave as IEEE, subnormal
+            // arguments and results flush to zero; PTX ISA "rcp/sqrt/rsqrt.approx.ftz.f32"): an IEEE divide costs
+            // ~21 FFMA issue slots on sm_100, these cost one MUFU (the non-ftz forms add 3-6 fix-up instructions).
+            case NGB200_OP_SQRT:
+                if (approx) return "ngb_sqrt(" + a + ")";
+                return faithful ? rn("sqrt") + "(" + a + ")" : std::string("sqrt") + sfx + "(" + a + ")";
             case NGB200_OP_RSQRT:
+                if (approx) return "ngb_rsqrt(" + a + ")";
+                if (!faithful && f64) return "rsqrt(" + a + ")";
                 return faithful ? rn("div") + "(T(1), " + rn("sqrt") + "(" + a + "))"
                                 : std::string("T(1) / sqrt") + sfx + "(" + a + ")";
-            case NGB200_OP_RCP: return faithful ? rn("div") + "(T(1), " + a + ")" : "T(1) / " + a;
+            case NGB200_OP_RCP:
+                if (approx) return "ngb_rcp(" + a + ")";
+                return faithful ? rn("div") + "(T(1), " + a + ")" : "T(1) / " + a;
             case NGB200_OP_ABS: return std::string("fabs") + sfx + "(" + a + ")";
             case NGB200_OP_NAN_TO_NUM: return "ngb_nan_to_num(" + a + ", " + b + ")";
             case NGB200_OP_FMA: return std::string("fma") + sfx + "(" + a + ", " + b + ", " + c + ")";
@@ -364,9 +384,9 @@ struct Gen {
             case NGB200_OP_FMA: return "__ffma2_rn(" + a + ", " + b + ", " + c + ")";
             case NGB200_OP_NEG: return "ngb_neg2(" + a + ")";
             case NGB200_OP_DIV: return both(faithful ? "__fdiv_rn($a, $b)" : "$a / $b");
-            case NGB200_OP_SQRT: return both(faithful ? "__fsqrt_rn($a)" : "sqrtf($a)");
-            case NGB200_OP_RSQRT: return both(faithful ? "__fdiv_rn(1.0f, __fsqrt_rn($a))" : "1.0f / sqrtf($a)");
-            case NGB200_OP_RCP: return both(faithful ? "__fdiv_rn(1.0f, $a)" : "1.0f / $a");
+            case NGB200_OP_SQRT: return both(approx ? "ngb_sqrt($a)" : faithful ? "__fsqrt_rn($a)" : "sqrtf($a)");
+            case NGB200_OP_RSQRT: return both(approx ? "ngb_rsqrt($a)" : faithful ? "__fdiv_rn(1.0f, __fsqrt_rn($a))" : "1.0f / sqrtf($a)");
+            case NGB200_OP_RCP: return both(approx ? "ngb_rcp($a)" : faithful ? "__fdiv_rn(1.0f, $a)" : "1.0f / $a");
             case NGB200_OP_ABS: return both("fabsf($a)");
             case NGB200_OP_NAN_TO_NUM: return both("ngb_nan_to_num($a, $b)");
             case NGB200_OP_EXP: return both("expf($a)");
@@ -435,6 +455,31 @@ struct Gen {
             for (int j = 0; j < k; ++j) want_slot(ops[j]);
         }
         for (const ngb200_store &s : P.stores) want_slot(s.value);
+        // register demand: the largest number of per-item values alive at once when the program runs in IR order
+        // (inputs become live at their first use, stored values stay live to the end)
+        {
+            std::vector<int> first_use(n, -1), last_use(n, -1), delta(n + 2, 0);
+            for (int v = 0; v < n; ++v) {
+                if (!live[v]) continue;
+                const ngb200_instr &I = P.instr[v];
+                const int k = n_operands_of(I.op);
+                const int ops[3] = {I.a, I.b, I.c};
+                for (int j = 0; j < k; ++j) {
+                    if (first_use[ops[j]] < 0) first_use[ops[j]] = v;
+                    last_use[ops[j]] = v;
+                }
+            }
+            for (const ngb200_store &s : P.stores) last_use[s.value] = n;
+            for (int v = 0; v < n; ++v) {
+                if (!live[v] || uniform[v] || last_use[v] < 0) continue;
+                const int start = P.instr[v].op == NGB200_OP_INPUT ? (first_use[v] < 0 ? n : first_use[v]) : v;
+                delta[start] += 1;
+                delta[last_use[v]] -= 1;
+            }
+            int cur = 0;
+            max_live = 0;
+            for (int v = 0; v <= n; ++v) { cur += delta[v]; if (cur > max_live) max_live = cur; }
+        }
         xoff.assign(P.in_width.size(), 0);
         for (size_t k = 0; k < P.in_width.size(); ++k) {
             xoff[k] = NX;
@@ -457,6 +502,10 @@ struct Gen {
                 pair ? ", packed f32x2" : "");
         appendf(s, "typedef %s T;\ntypedef %s VT;\n", T, VT);
         appendf(s, "#define NGB_V %d\n#define NGB_TPB %d\n", vec, P.tpb);
+        // an explicit minimum of 1 CTA/SM makes ptxas spend up to 255 registers (measured 116 -> 207): only state a
+        // minimum when it is a real cap
+        if (P.minb > 1 && 65536 / (P.tpb * P.minb) < 255) appendf(s, "#define NGB_BOUNDS __launch_bounds__(NGB_TPB, %d)\n", P.minb);
+        else s += "#define NGB_BOUNDS __launch_bounds__(NGB_TPB)\n";
         s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
         appendf(s, "struct Params { Operand in[%d]; Operand out[%d]; double scal[%d]; long long n; };\n",
                 nin > 0 ? nin : 1, nout > 0 ? nout : 1, P.n_params > 0 ? P.n_params : 1);
@@ -464,6 +513,11 @@ struct Gen {
             s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysign(1.7976931348623157e308, a) : a); }\n";
         else
             s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysignf(3.4028234663852886e38f, a) : a); }\n";
+        if (approx) {
+            s += "__device__ __forceinline__ float ngb_rcp(float a) { float r; asm(\"rcp.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+            s += "__device__ __forceinline__ float ngb_sqrt(float a) { float r; asm(\"sqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+            s += "__device__ __forceinline__ float ngb_rsqrt(float a) { float r; asm(\"rsqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+        }
         const char *ld = ldmode == 0 ? "*" : ldmode == 1 ? "__ldg" : ldmode == 2 ? "__ldcs" : "__ldlu";
         appendf(s, "#define NGB_LD(p) %s(p)\n", ld);
         if (stmode == 0) s += "#define NGB_ST(p, v) (*(p) = (v))\n";
@@ -527,7 +581,7 @@ struct Gen {
         }
 
         // ---- scalar kernel: any strides, gather/scatter -----------------------------------
-        appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_scalar(const Params p) {\n");
+        appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_scalar(const Params p) {\n");
         appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
         s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
         s += "  for (long long i = (long long)blockIdx.x * NGB_TPB + threadIdx.x; i < p.n; i += stride) {\n";
@@ -556,7 +610,7 @@ struct Gen {
         if (vec > 1 && pair) {
             // items (0,1) and (2,3) of each thread's vector are processed as float2 pairs
             const int npair = vec / 2;
-            appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_vec(const Params p) {\n");
+            appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_vec(const Params p) {\n");
             appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
             s += "  const long long nvec = p.n / NGB_V;\n";
             s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
@@ -580,7 +634,7 @@ struct Gen {
                 }
             s += "  }\n}\n";
         } else if (vec > 1) {
-            appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_vec(const Params p) {\n");
+            appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_vec(const Params p) {\n");
             appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
             s += "  const long long nvec = p.n / NGB_V;\n";
             s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
@@ -720,9 +774,27 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     if (vec > vmax) vec = vmax;
     if (vec == 3) vec = 2;
     if (P->any_indexed || gen.NX == 0) vec = 1;
-    const bool pair = f32 && vec >= 2 && env_int("NGB200_PAIR", 1);
+    // Packed f32x2 arithmetic: measured on B200 (scripts/micro/fp32_rate.cu) scalar FFMA already issues at the full
+    // 128 lanes/clk/SM (34.4 T FMA/s) and FFMA2 reaches the same 70 TFLOP/s, so packing buys no throughput and costs
+    // registers in large programs; it is kept for the small HBM-bound programs (half the issue slots per item).
+    const bool pair = f32 && vec >= 2 && env_int("NGB200_PAIR", small ? 1 : 0);
     P->vec = vec;
-    P->tpb = env_int("NGB200_TPB", 256);
+    // Register budget of LARGE programs.  ptxas schedules a long straight-line body for maximal ILP and can take
+    // 200+ registers for a chain whose working set is 17 values (measured: exp->normalized->log, 205 registers,
+    // 11.1 ms; capped at 48: 5.4 ms; the gathered physics kernels: 254 -> 128 registers, +15%).  The cap is derived
+    // from the program's own peak number of live values; small (HBM-bound) programs keep ptxas' natural choice.
+    // Programs that need more than 128 registers run 128-thread CTAs: finer occupancy granularity (CGA full x full,
+    // 2 items/thread: 168 registers -> 3 CTAs of 128 instead of 1 CTA of 256, 4.33 vs 5.86 ms).
+    P->minb = 1;
+    P->tpb = 256;
+    if (live_guess >= 256) {
+        const int need = gen.max_live * (f32 ? 1 : 2) * vec + 16;
+        if (need > 128) P->tpb = 128;
+        int minb = 65536 / (P->tpb * need);
+        P->minb = minb < 1 ? 1 : (minb > 8 ? 8 : minb);
+    }
+    if (env_int("NGB200_TPB", 0) > 0) P->tpb = env_int("NGB200_TPB", 0);
+    if (env_int("NGB200_MINBLOCKS", 0) > 0) P->minb = env_int("NGB200_MINBLOCKS", 0);
     P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform, pair);
     P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
@@ -886,7 +958,11 @@ extern "C" int ngb200_operator_create(const int32_t *terms, int32_t n_terms, int
     return ngb200_program_create(&d, out);
 }
 
-extern "C" void ngb200_program_destroy(ngb200_program *P) { delete P; }
+extern "C" void ngb200_program_destroy(ngb200_program *P) {
+    if (!P) return;
+    host_pipe_destroy(P->host);
+    delete P;
+}
 
 extern "C" const char *ngb200_program_source(const ngb200_program *P) { return P ? P->source.c_str() : ""; }
 
@@ -1035,44 +1111,49 @@ extern "C" int ngb200_host_free(void *ptr) {
     return NGB200_OK;
 }
 
-namespace {
-struct Slot {
-    CUstream stream = nullptr;
-    std::vector<CUdeviceptr> in, out;
-};
-struct HostRun {
+// Staging resources of the host path, kept with the program between calls (allocating / freeing device memory
+// on every call serialises the device and made the pipeline's throughput erratic): per slot one stream and one
+// device chunk buffer per operand, plus the device copies of broadcast operands.
+struct HostPipe {
+    int device = -1;
+    int64_t chunk_items = 0;
+    struct Slot {
+        CUstream stream = nullptr;
+        std::vector<CUdeviceptr> in, out;
+    };
     std::vector<Slot> slots;
     std::vector<CUdeviceptr> bcast;
-    ~HostRun() {
+    void release() {
         for (Slot &s : slots) {
             for (CUdeviceptr p : s.in) if (p) g_drv.p_cuMemFree(p);
             for (CUdeviceptr p : s.out) if (p) g_drv.p_cuMemFree(p);
             if (s.stream) g_drv.p_cuStreamDestroy(s.stream);
         }
         for (CUdeviceptr p : bcast) if (p) g_drv.p_cuMemFree(p);
+        slots.clear();
+        bcast.clear();
+        chunk_items = 0;
+        device = -1;
     }
 };
-}  // namespace
+
+static void host_pipe_destroy(HostPipe *h) {
+    if (!h) return;
+    if (g_drv.ok) h->release();
+    delete h;
+}
 
 // copy `items` batch items of one operand between host layout and a device SoA/AoS chunk buffer
 static int copy_chunk(bool to_device, const ngb200_operand &h, int width, int es, int64_t first, int64_t items,
                       CUdeviceptr d, int64_t d_cs, CUstream s) {
     if (width == 0 || items == 0) return NGB200_OK;
-    if (h.batch_stride == 1) {  // SoA on the host: one row per component
-        CUDA_MEMCPY2D c;
-        memset(&c, 0, sizeof c);
-        c.WidthInBytes = (size_t)items * es;
-        c.Height = (size_t)width;
-        char *hp = (char *)h.ptr + first * es;
-        if (to_device) {
-            c.srcMemoryType = CU_MEMORYTYPE_HOST; c.srcHost = hp; c.srcPitch = (size_t)h.comp_stride * es;
-            c.dstMemoryType = CU_MEMORYTYPE_DEVICE; c.dstDevice = d; c.dstPitch = (size_t)d_cs * es;
-        } else {
-            c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = hp; c.dstPitch = (size_t)h.comp_stride * es;
-            c.srcMemoryType = CU_MEMORYTYPE_DEVICE; c.srcDevice = d; c.srcPitch = (size_t)d_cs * es;
+    if (h.batch_stride == 1) {  // SoA on the host: one contiguous row per component -> one 1-D DMA per row
+        for (int c = 0; c < width; ++c) {
+            char *hp = (char *)h.ptr + ((int64_t)c * h.comp_stride + first) * es;
+            CUdeviceptr dp = d + (size_t)c * d_cs * es;
+            if (to_device) CU(cuMemcpyHtoDAsync(dp, hp, (size_t)items * es, s));
+            else CU(cuMemcpyDtoHAsync(hp, dp, (size_t)items * es, s));
         }
-        if (width == 1) { c.srcPitch = c.dstPitch = c.WidthInBytes; }
-        CU(cuMemcpy2DAsync(&c, s));
         return NGB200_OK;
     }
     if (h.comp_stride == 1 && h.batch_stride == width) {  // AoS on the host: one contiguous block
@@ -1099,27 +1180,35 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
     int64_t per_item = 0;
     for (size_t k = 0; k < nin; ++k) if (P->in_mode[k] == NGB200_VARYING) per_item += P->in_width[k] * es;
     for (size_t k = 0; k < nout; ++k) per_item += P->out_width[k] * es;
-    if (chunk_items <= 0) chunk_items = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 64) * (1 << 20) / (per_item ? per_item : 1);
+    if (chunk_items <= 0) chunk_items = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 128) * (1 << 20) / (per_item ? per_item : 1);
     chunk_items = (chunk_items + 255) / 256 * 256;
     if (chunk_items > batch) chunk_items = (batch + 255) / 256 * 256;
     const int n_slots = (int)std::min<int64_t>(env_int("NGB200_HOST_STREAMS", 4), (batch + chunk_items - 1) / chunk_items);
 
-    HostRun run;
-    run.slots.resize(n_slots);
-    run.bcast.assign(nin, 0);
-    for (Slot &s : run.slots) {
-        CU(cuStreamCreate(&s.stream, CU_STREAM_NON_BLOCKING));
-        s.in.assign(nin, 0);
-        s.out.assign(nout, 0);
+    std::lock_guard<std::mutex> pipe_lock(P->host_mu);      // one host run per program at a time (shared staging)
+    if (!P->host) P->host = new HostPipe;
+    HostPipe &run = *P->host;
+    if (run.device != dev || run.chunk_items != chunk_items || (int)run.slots.size() != n_slots) {
+        run.release();
+        run.device = dev;
+        run.chunk_items = chunk_items;
+        run.slots.resize(n_slots);
+        run.bcast.assign(nin, 0);
+        for (HostPipe::Slot &s : run.slots) {
+            CU(cuStreamCreate(&s.stream, CU_STREAM_NON_BLOCKING));
+            s.in.assign(nin, 0);
+            s.out.assign(nout, 0);
+            for (size_t k = 0; k < nin; ++k)
+                if (P->in_mode[k] == NGB200_VARYING && P->in_width[k]) CU(cuMemAlloc(&s.in[k], (size_t)chunk_items * P->in_width[k] * es));
+            for (size_t k = 0; k < nout; ++k)
+                if (P->out_width[k]) CU(cuMemAlloc(&s.out[k], (size_t)chunk_items * P->out_width[k] * es));
+        }
         for (size_t k = 0; k < nin; ++k)
-            if (P->in_mode[k] == NGB200_VARYING && P->in_width[k]) CU(cuMemAlloc(&s.in[k], (size_t)chunk_items * P->in_width[k] * es));
-        for (size_t k = 0; k < nout; ++k)
-            if (P->out_width[k]) CU(cuMemAlloc(&s.out[k], (size_t)chunk_items * P->out_width[k] * es));
+            if (P->in_mode[k] == NGB200_BROADCAST && P->in_width[k]) CU(cuMemAlloc(&run.bcast[k], (size_t)P->in_width[k] * es));
     }
     // broadcast operands: one small upload, visible to all streams after a sync
     for (size_t k = 0; k < nin; ++k) {
         if (P->in_mode[k] != NGB200_BROADCAST || !P->in_width[k]) continue;
-        CU(cuMemAlloc(&run.bcast[k], (size_t)P->in_width[k] * es));
         std::vector<char> packed((size_t)P->in_width[k] * es);
         for (int c = 0; c < P->in_width[k]; ++c) memcpy(&packed[(size_t)c * es], (char *)in[k].ptr + (size_t)c * in[k].comp_stride * es, es);
         CU(cuMemcpyHtoDAsync(run.bcast[k], packed.data(), packed.size(), run.slots[0].stream));
@@ -1128,7 +1217,7 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
     std::vector<ngb200_operand> din(nin ? nin : 1), dout(nout);
     int64_t chunk_index = 0;
     for (int64_t first = 0; first < batch; first += chunk_items, ++chunk_index) {
-        Slot &s = run.slots[chunk_index % n_slots];
+        HostPipe::Slot &s = run.slots[chunk_index % n_slots];
         int64_t items = std::min(chunk_items, batch - first);
         for (size_t k = 0; k < nin; ++k) {
             if (P->in_mode[k] == NGB200_BROADCAST) { din[k] = {(void *)run.bcast[k], 1, 0, nullptr}; continue; }
@@ -1148,7 +1237,7 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
             if (rc) return rc;
         }
     }
-    for (Slot &s : run.slots) CU(cuStreamSynchronize(s.stream));
+    for (HostPipe::Slot &s : run.slots) CU(cuStreamSynchronize(s.stream));
     return NGB200_OK;
 }
 

@@ -145,9 +145,31 @@ class Trace:
             return f
         if self.is_const(b, 1.0):
             return a
+        if not self.faithful:
+            # FAST programs: a / b = a * (1 / b).  The reciprocal is hash-consed, so the components of a multivector
+            # divided by one scalar share ONE reciprocal, and the multiplies fuse into FMAs downstream.
+            return self.mul(a, self.rcp(b))
         if self.is_const(a, 1.0):
             return self._emit(rt.OP_RCP, b)
         return self._emit(rt.OP_DIV, a, b)
+
+    def rcp(self, b):
+        """1 / b with the exact-enough rewrites of FAST mode: 1/(c*y) = (1/c) * (1/y), 1/sqrt(x) = rsqrt(x)."""
+        f = self._fold(lambda x: 1 / x, b)
+        if f is not None:
+            return f
+        op, x, y, _ = self.instr[b]
+        if not self.faithful:
+            if op == rt.OP_SQRT:
+                return self._emit(rt.OP_RSQRT, x)
+            if op == rt.OP_MUL:
+                for c, other in ((x, y), (y, x)):
+                    cv = self.const_value(c)
+                    if cv is not None and cv != 0 and np.isfinite(cv):
+                        return self.mul(self.const(1.0 / cv), self.rcp(other))
+            if op == rt.OP_NEG:
+                return self.neg(self.rcp(x))
+        return self._emit(rt.OP_RCP, b)
 
     def unary(self, op, a, fn=None):
         if fn is not None:
@@ -176,7 +198,7 @@ class Trace:
         if p == 1:
             return a
         if p == -1:
-            return self.div(self.const(1.0), a)
+            return self.rcp(a)
         if p == 2:
             return self.mul(a, a)
         raise NotImplementedError(f'power {p} is not supported in traced code')

@@ -6,7 +6,7 @@ from numga_b200 import B200Context
 from bench import device_mv
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'sandwich'
-launches = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+launches = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 4
 if which == 'sandwich':
     ctx = B200Context((3, 0, 1)); S = ctx.subspace
     R = ctx.multivector.motor(np.random.default_rng(1).standard_normal(8).astype(np.float32))
@@ -24,6 +24,30 @@ elif which in ('roundtrip', 'roundtrip64'):
     ctx = B200Context((3, 0, 1), dtype=torch.float64 if which.endswith('64') else torch.float32)
     bv = device_mv(ctx, ctx.subspace.bivector(), 1 << 24, 7, 0, scale=0.5)
     f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv)
+if which == 'physics_time':
+    import json
+    from bench import physics_config, measured_peaks
+    r = physics_config(torch, B200Context, 0, measured_peaks()[0], torch.float64 if 'f64' in sys.argv else torch.float32, 'fp')
+    print(which, {k: v for k, v in os.environ.items() if k.startswith('NGB200') and 'CACHE' not in k}, f"{r['ms']:.3f} ms {r['items_per_s']/1e9:.3f} G/s {r['achieved_gbs']:.0f} GB/s")
+    sys.exit(0)
+if which == 'cga_pitch':
+    from bench import time_steps
+    ctx = B200Context((4, 1, 0)); F = ctx.subspace.full(); n = 1 << 26
+    from numga_b200 import runtime as rt
+    for pad in (0, 32, 96, 256 + 32, 1024 + 32, 4096 + 32, 65536 + 32, 3 * 65536 + 96):
+        def mk(seed):
+            t = torch.empty((32, n + pad), dtype=torch.float32, device='cuda')
+            for c in range(32):
+                rt.fill_normal(t[c].data_ptr(), n, seed=seed * 1000 + c, stream=torch.cuda.current_stream().cuda_stream)
+            return t
+        ta, tb, to = mk(5), mk(6), torch.empty((32, n + pad), dtype=torch.float32, device='cuda')
+        a = ctx.multivector(values=ta[:, :n].movedim(0, -1), subspace=F); b = ctx.multivector(values=tb[:, :n].movedim(0, -1), subspace=F)
+        f = ctx.jit(lambda x, y: x * y)
+        o = ctx.multivector(values=to[:, :n].movedim(0, -1), subspace=F)
+        ms = time_steps(lambda: f(a, b, out=(o,)), 10, 3)
+        print(which, 'pad', pad, f'{ms:.3f} ms {384*n/ms/1e6:.0f} GB/s', flush=True)
+        del ta, tb, to, a, b, o
+    sys.exit(0)
 if which in ('cga_time', 'roundtrip_time'):
     import time
     from bench import time_steps

@@ -269,3 +269,27 @@ def test_config4_cga_full_product_16M_associativity_with_scalar():
     assert torch.equal(((a * 4.0) * b).values, ab.values * 4)          # bilinearity, exact for powers of two
     rev = (~b) * (~a)                                                  # ~(ab) = ~b ~a
     assert _rel_err((~ab).numpy()[:4096], rev.numpy()[:4096]) < 1e-5
+
+
+def test_cuda_graph_capture_of_an_operator_chain():
+    """B200Context.capture: a chain of eager + jitted kernels recorded into one CUDA graph replays to the same
+    result, and follows in-place updates of its input buffers."""
+    ctx = _ctx((3, 0, 1), np.float32)
+    rng = np.random.default_rng(21)
+    n = 5000
+    b = ctx.multivector.bivector((0.4 * rng.standard_normal((n, 6))).astype(np.float32))
+    p = ctx.multivector.antivector(rng.standard_normal((n, 4)).astype(np.float32))
+    spin = ctx.jit(lambda m, x: m.normalized() >> x)
+
+    def chain(b, p):
+        m = b.exp()                  # eager fused kernel
+        m = m * m                    # eager product
+        return spin(m, p) + p        # jitted kernel + eager combine
+    want = chain(b, p).numpy()
+    g = ctx.capture(chain, b, p)
+    assert g.n_kernels == 4
+    assert np.array_equal(g.replay().numpy(), want)
+    b2 = (0.4 * rng.standard_normal((n, 6))).astype(np.float32)
+    want2 = chain(ctx.multivector.bivector(b2), p).numpy()
+    b.values.copy_(torch.as_tensor(b2, device='cuda'))
+    assert np.array_equal(g.replay().numpy(), want2)
