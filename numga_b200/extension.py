@@ -318,3 +318,82 @@ def _exp_bisect(b, n=BISECTION_STEPS):
     for _ in range(n):
         m = m.squared()
     return m
+
+
+# ---- decompositions (decompose.py) ----------------------------------------------------------------------------------
+decompose_polar = new_dispatch('decompose_polar', 'b = L * s: polar decomposition into a bivector line and a Study number (PGA4CS eq 68-70)')
+
+
+@decompose_polar.register(lambda s: s.inside.bivector() and s.squared().inside.study())
+def _decompose_polar(b):
+    s = b.symmetric_reverse_product().square_root()
+    si = s.inverse().nan_to_num(0)
+    return b.bivector_product(si), s
+
+
+decompose_invariant = new_dispatch('decompose_invariant', 'b = l + r with l.inner(r) = 0 and l*l, r*r scalar')
+
+
+@decompose_invariant.register(lambda s: s.inside.bivector() and s.squared().inside.scalar())
+def bivector_decompose_simple(b):
+    return b, b.context.multivector.empty()
+
+
+@decompose_invariant.register(lambda s: s.inside.bivector() and s.squared().is_study)
+def bivector_decompose_bisimple(b):
+    """decompose.py:49-53."""
+    b2 = b.squared()
+    s = b2.study_conjugate() / (b2.study_norm() * 2)
+    return (1 / 2 + s).bivector_product(b), (1 / 2 - s).bivector_product(b)
+
+
+motor_translator = new_dispatch('motor_translator', 'Translator part of a motor')
+
+
+@motor_translator.register(lambda m: m.inside.rotor())
+def rotor_translator(r):
+    """A pure rotor has no translator part: the identity."""
+    return r.context.multivector.scalar()
+
+
+@motor_translator.register(lambda m: m.inside.motor())
+def _motor_translator(m):
+    op = m.context.operator.euclidian_factorization(m.subspace)
+    return 1 + op(m, m)
+
+
+motor_rotor = new_dispatch('motor_rotor', 'Rotor part of a motor')
+
+
+@motor_rotor.register(lambda m: m.inside.rotor())
+def rotor_rotor(r):
+    return r
+
+
+@motor_rotor.register(lambda m: m.inside.motor())
+def _motor_rotor(m):
+    return m.nondegenerate()
+
+
+motor_split = new_dispatch('motor_split', 'Split a motor w.r.t. an origin o into (t, r): r leaves o invariant, t is the shortest path')
+
+
+@motor_split.register(lambda m, o: m.inside.motor() and o.inside.antivector() and o.dual().is_degenerate)
+def motor_split_euclidian(m, o):
+    """o is the euclidean origin: m = t * r with the closed forms above (decompose.py:84-90)."""
+    return m.motor_translator(), m.motor_rotor()
+
+
+@motor_split.register(lambda m, o: m.inside.motor() and o.inside.antivector() and o.is_blade)
+def motor_split_blade(m, o):
+    """o is a single blade: drop the axes that cannot occur (decompose.py:91-99)."""
+    R = m.subspace.reject(o.subspace.dual())
+    T = m.context.subspace.vector().product(o.subspace.dual())
+    t, r = _motor_split(m, o)
+    return t.select_subspace(T), r.select_subspace(R)
+
+
+@motor_split.register(lambda m, o: m.inside.motor() and o.inside.antivector())
+def _motor_split(m, o):
+    t = ((m >> o) / o).motor_square_root()        # shortest trajectory from o to m >> o
+    return t, ~t * m                               # the residual is a rotation that leaves o invariant

@@ -314,6 +314,12 @@ class OperatorFactory:
         p = self.symmetric_reverse_product(x)
         return self.geometric_product(p, self.scalar_negation(p)).symmetry((0, 1, 2, 3))
 
+    def euclidian_factorization(self, m) -> Operator:
+        """Translational bivector part of a motor w.r.t. the euclidean origin: <dual(m * dual(m))>_2, both slots
+        identical (factory.py:627-633); uncached like the reference."""
+        op = self.geometric_product(m, self.right_hodge(m))
+        return self.right_hodge(op).select_grade(2).symmetry((0, 1))
+
     @cache
     def inertia(self, l, r) -> Operator:
         """l v (l x r): maps rates to momenta for points l (factory.py:599-602)."""

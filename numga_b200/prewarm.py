@@ -1,34 +1,27 @@
 """Compile (NVRTC, sm_100a) the generated kernels of the standard programs into the in-tree cubin cache.
 
-Runs without a GPU: contexts are created in compile-only mode, the expressions of the case catalogue
-(tests/cases.py, if present) and of bench.py are executed on uninitialised host tensors so that every
-kernel they need — per-method eager kernels, fused `jit` kernels, operator-table kernels — is generated,
-compiled and stored under numga_b200/_kcache/.  On the GPU box these are cache hits (no JIT there).
+Runs without a GPU: contexts are created in compile-only mode and the expressions of the case catalogue
+(tests/cases.py), of bench.py, of the physics example and of the ported reference identity tests are executed on
+uninitialised host tensors, so that every kernel they need — per-method eager kernels, fused `jit` kernels,
+operator-table kernels — is generated, compiled and stored under numga_b200/_kcache/.  On the GPU box these are
+cache hits (no JIT there).  The work is a list of independent jobs spread over a process pool (the cache is written
+atomically, so workers never collide).
 """
 import os
 import sys
 
-import numpy as np
-import torch
-
-from numga_b200 import runtime as rt
-from numga_b200.backend import B200Context
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _cases():
-    tests = os.path.join(ROOT, 'tests')
-    if not os.path.isdir(tests):
-        return []
-    if tests not in sys.path:
-        sys.path.insert(0, tests)
-    from cases import CASES
-    return CASES
+def _paths():
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
 
 def bench_programs(ctx_of):
     """The fused programs bench.py times (kept in one place so build() and bench agree)."""
+    import torch
     out = []
     pga32 = ctx_of((3, 0, 1), torch.float32, 'fast')
     S = pga32.subspace
@@ -43,7 +36,8 @@ def bench_programs(ctx_of):
     return out
 
 
-def prewarm(batch=8):
+def _ctx_factory():
+    from numga_b200.backend import B200Context
     contexts = {}
 
     def ctx_of(pqr, dtype, mode):
@@ -51,39 +45,86 @@ def prewarm(batch=8):
         if key not in contexts:
             contexts[key] = B200Context(pqr, dtype=dtype, mode=mode, device='cpu', compile_only=True)
         return contexts[key]
+    return ctx_of
 
-    before = len(os.listdir(rt_cache_dir())) if os.path.isdir(rt_cache_dir()) else 0
 
-    def run(ctx, fn, specs):
-        mvs = []
-        for sub, kind in specs:
-            shape = (batch, len(sub)) if kind == 'batch' else (len(sub),)
-            mvs.append(ctx.multivector(values=torch.zeros(shape, dtype=ctx.dtype), subspace=sub))
-        fn(*mvs)              # eager: one kernel per method call
-        ctx.jit(fn)(*mvs)     # fused: one kernel for the whole expression
+def _run(ctx, fn, specs, batch=8):
+    import torch
+    mvs = []
+    for sub, kind in specs:
+        shape = (batch, len(sub)) if kind == 'batch' else (len(sub),)
+        mvs.append(ctx.multivector(values=torch.zeros(shape, dtype=ctx.dtype), subspace=sub))
+    fn(*mvs)              # eager: one kernel per method call
+    ctx.jit(fn)(*mvs)     # fused: one kernel for the whole expression
 
-    for name, pqr, specs, scale, fn in _cases():
+
+def jobs():
+    """(kind, argument) pairs; every job is independent of the others."""
+    _paths()
+    out = [('bench', None)]
+    out += [('physics', (dt, mode)) for dt in ('float32', 'float64') for mode in ('fast', 'faithful')]
+    if os.path.isdir(os.path.join(ROOT, 'tests')):
+        from cases import CASES
+        out += [('case', c[0]) for c in CASES]
+        import test_reference_identities as T
+        for k, (fn, params) in enumerate(T.GPU_MATRIX):
+            out += [('identity', (k, descr)) for descr in params]
+        out += [('identity_single', k) for k in range(len(T.GPU_SINGLES))]
+    # biggest first: the 5-dimensional inverse sweeps dominate the wall clock
+    weight = lambda j: -(sum(j[1][1]) if j[0] == 'identity' else 0)
+    return sorted(out, key=weight)
+
+
+def run_job(job):
+    _paths()
+    import torch
+    kind, arg = job
+    ctx_of = _ctx_factory()
+    if kind == 'bench':
+        for ctx, fn, specs in bench_programs(ctx_of):
+            _run(ctx, fn, specs)
+    elif kind == 'physics':
+        # rigid-body physics (config 5): the generic per-method kernels and the six fused kernels of a sub-step
+        from numga_b200.examples.physics import FusedStep, setup_bodies
+        ctx = ctx_of('x+y+z+w0', getattr(torch, arg[0]), arg[1])
+        bodies, sets = setup_bodies(ctx, n_bodies=12)
+        bodies.integrate(1 / 200, sets)
+        FusedStep(bodies, sets).integrate(bodies, 1 / 200)
+        bodies.kinetic_energy()
+    elif kind == 'case':
+        from cases import CASE_BY_NAME
+        name, pqr, specs, scale, fn = CASE_BY_NAME[arg]
         for dtype in (torch.float32, torch.float64):
             for mode in ('fast', 'faithful'):
                 ctx = ctx_of(pqr, dtype, mode)
-                run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
-    for ctx, fn, specs in bench_programs(ctx_of):
-        run(ctx, fn, specs)
-    # rigid-body physics (config 5): the generic per-method kernels and the six fused kernels of a sub-step
-    from numga_b200.examples.physics import FusedStep, setup_bodies
-    for dtype in (torch.float32, torch.float64):
-        for mode in ('fast', 'faithful'):
-            ctx = ctx_of('x+y+z+w0', dtype, mode)
-            bodies, sets = setup_bodies(ctx, n_bodies=12)
-            bodies.integrate(1 / 200, sets)
-            FusedStep(bodies, sets).integrate(bodies, 1 / 200)
-            bodies.kinetic_energy()
-    after = len(os.listdir(rt_cache_dir())) if os.path.isdir(rt_cache_dir()) else 0
-    return max(after, before) // 2
+                _run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
+    elif kind == 'identity':
+        import test_reference_identities as T
+        T.GPU_MATRIX[arg[0]][0](arg[1], 'compile')
+    elif kind == 'identity_single':
+        import test_reference_identities as T
+        T.GPU_SINGLES[arg]('compile')
+    return job
 
 
 def rt_cache_dir():
     return os.environ.get('NGB200_CACHE_DIR') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '_kcache')
+
+
+def prewarm(workers=None):
+    """Returns the number of cubins in the cache afterwards."""
+    import multiprocessing as mp
+    todo = jobs()
+    workers = workers or max(1, min(len(todo), os.cpu_count() or 1, 16))
+    if workers == 1:
+        for j in todo:
+            run_job(j)
+    else:
+        with mp.get_context('spawn').Pool(workers) as pool:
+            for _ in pool.imap_unordered(run_job, todo, chunksize=1):
+                pass
+    d = rt_cache_dir()
+    return len([f for f in os.listdir(d) if f.endswith('.cubin')]) if os.path.isdir(d) else 0
 
 
 if __name__ == '__main__':

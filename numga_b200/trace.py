@@ -277,6 +277,8 @@ class SymArray:
             if arr.dtype == object:
                 return None
             regs = [self.trace.const(v) for v in arr.reshape(-1)]
+        if len(self.regs) == 0 and len(regs) <= 1 or len(regs) == 0 and len(self.regs) <= 1:
+            return [], []                       # an empty multivector (no components) stays empty
         n = max(len(regs), len(self.regs))
         mine = self.regs * n if len(self.regs) == 1 else self.regs
         regs = regs * n if len(regs) == 1 else regs

@@ -1,0 +1,223 @@
+"""The reference's own floating-point identity tests, ported to the B200 backend with the same signatures, sample
+counts and tolerances (fp64, atol 1e-9 unless the reference states otherwise):
+  numga/multivector/extension/test/test_logexp.py:11-34      exp / motor_log round trip (bisection)
+  numga/multivector/extension/test/test_norms.py:10-62       Study numbers, normalization, 6d refusal
+  numga/multivector/extension/test/test_decompose.py         invariant decomposition, translator/rotor, motor_split
+  numga/multivector/extension/test/test_roots.py             motor square roots
+  numga/multivector/extension/test/test_inverse.py           inverses of grade combinations
+
+GPU tier: the real kernels.  CPU tier: a few signatures through the numpy interpretation of the traced IR
+(tests/cpu_emulation.py), which checks the host logic and the traced programs without a GPU.
+"""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from refutil import assert_close, random_motor, random_non_motor, random_subspace, values_of
+
+
+@contextlib.contextmanager
+def _context(descr, where, dtype=torch.float64):
+    if where == 'gpu':
+        from numga_b200 import B200Context
+        yield B200Context(descr, dtype=dtype, device='cuda:0')
+    elif where == 'compile':        # numga_b200/prewarm.py: generate + compile every kernel of the test, no execution
+        from numga_b200 import B200Context
+        yield B200Context(descr, dtype=dtype, device='cpu', compile_only=True)
+    else:
+        from cpu_emulation import emulate_launches, emulated_context
+        with emulate_launches():
+            yield emulated_context(descr, dtype, mode='fast')
+
+
+def _params(descrs, cpu_subset):
+    out = [pytest.param(d, 'gpu', marks=pytest.mark.gpu, id=f'{d}-gpu') for d in descrs]
+    return out + [pytest.param(d, 'cpu', id=f'{d}-cpu') for d in cpu_subset]
+
+
+LOGEXP = [(2, 0, 0), (1, 0, 1), (1, 1, 0), (3, 0, 0), (2, 0, 1), (2, 1, 0), (1, 1, 1), (1, 0, 2), (4, 0, 0), (3, 0, 1),
+          (3, 1, 0), (2, 1, 1), (2, 0, 2), (5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1)]
+
+
+@pytest.mark.parametrize('descr,where', _params(LOGEXP, [(3, 0, 1), (4, 1, 0)]))
+def test_bisect(descr, where):
+    """test_logexp.py:11-34: m.motor_log().exp() == m, also at a low iteration count."""
+    from numga_b200.extension import _exp_bisect, _motor_log_bisect  # noqa: F401
+    rng = np.random.RandomState(0)
+    with _context(descr, where) as ga:
+        m = random_motor(ga, (10,), rng)
+        assert_close(m, m.motor_log().exp())
+        low = ga.jit(lambda x: _exp_bisect(_motor_log_bisect(x, 2), 2))
+        assert_close(m, low(m))
+
+
+STUDY = [(2, 0, 0), (1, 0, 1), (1, 1, 0), (3, 0, 0), (2, 0, 1), (2, 1, 0), (1, 1, 1), (4, 0, 0), (3, 0, 1), (3, 1, 0),
+         (2, 1, 1), (2, 2, 0), (5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1), (3, 2, 0)]
+
+
+@pytest.mark.parametrize('descr,where', _params(STUDY, [(3, 0, 1), (5, 0, 0)]))
+def test_study(descr, where):
+    """test_norms.py:17-48."""
+    rng = np.random.RandomState(1)
+    with _context(descr, where) as ga:
+        m = random_non_motor(ga, (10,), rng=rng)
+        s = m.symmetric_reverse_product()
+        assert s.subspace.is_study
+        mn = m.normalized()
+        assert_close(mn * ~mn, 1)
+        assert_close(s.inverse() * s, 1)
+        rs = s.square_root()
+        assert_close(rs * rs, s)
+        assert_close((s * 0).square_root(), 0)
+        irs, irs2 = s.inverse().square_root(), s.square_root().inverse()
+        assert_close(irs2, irs, atol=1e-6)
+        assert_close(s * irs * irs, 1)
+
+
+def test_motor_normalize_6d_refused():
+    """test_norms.py:51-62: no known normalization in 6d -> dispatch raises (host logic only, no launch)."""
+    from numga_b200 import B200Context
+    ga = B200Context((6, 0, 0), dtype=torch.float64, device='cpu', compile_only=True)
+    m = ga.multivector(subspace=ga.subspace.even_grade(), values=np.ones((4, 32)))
+    assert not ga.subspace.even_grade().symmetric_reverse().is_study
+    with pytest.raises(Exception):
+        m.normalized()
+
+
+INVARIANT = [(2, 0, 0), (1, 0, 1), (1, 1, 0), (3, 0, 0), (2, 0, 1), (2, 1, 0), (1, 1, 1), (4, 0, 0), (3, 0, 1), (3, 1, 0),
+             (2, 1, 1), (2, 0, 2), (5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1)]
+
+
+@pytest.mark.parametrize('descr,where', _params(INVARIANT, [(3, 0, 1), (4, 0, 0)]))
+def test_invariant_decomposition(descr, where):
+    """test_decompose.py:11-38."""
+    rng = np.random.RandomState(1)
+    with _context(descr, where) as ga:
+        b = random_motor(ga, (10,), rng).select[2]
+        l, r = b.decompose_invariant()
+        assert_close(l.inner(r), 0)
+        assert_close(l.squared().select.nonscalar(), 0)
+        assert_close(r.squared().select.nonscalar(), 0)
+        assert_close(b, l + r)
+        L, R = l.exp(), r.exp()
+        assert_close(L * R, R * L)
+
+
+@pytest.mark.parametrize('descr,where', _params([(1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1)], [(3, 0, 1)]))
+def test_motor_decompose_euclidean(descr, where):
+    """test_decompose.py:41-55."""
+    rng = np.random.RandomState(2)
+    with _context(descr, where) as ga:
+        m = random_motor(ga, (10,), rng)
+        t, r = m.motor_translator(), m.motor_rotor()
+        assert_close(t * r, m)
+        assert_close((m * ~r).select.translator(), t)
+
+
+SPLIT = [(2, 0, 0), (3, 0, 0), (4, 0, 0), (5, 0, 0), (1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1), (1, 1, 0), (2, 1, 0),
+         (3, 1, 0), (4, 1, 0)]
+
+
+@pytest.mark.parametrize('descr,where', _params(SPLIT, [(3, 0, 1)]))
+def test_motor_split(descr, where):
+    """test_decompose.py:58-92: both for the canonical origin and an arbitrary point."""
+    rng = np.random.RandomState(10)
+    with _context(descr, where) as ga:
+        m = random_motor(ga, (10,), rng)
+        o = ga.multivector.basis()[-1].dual()
+        for origin in (o, random_motor(ga, (10,), rng) >> o):
+            t, r = m.motor_split(origin)
+            assert_close(t * r, m)
+            assert_close(r >> origin, origin, atol=1e-6)
+            assert_close(t * ~t, 1, atol=1e-6)
+            assert_close(r * ~r, 1, atol=1e-6)
+            assert_close(t.motor_log().inner(r.motor_log()), 0)
+
+
+ROOTS = [(2, 0, 0), (1, 0, 1), (3, 0, 0), (2, 0, 1), (4, 0, 0), (3, 0, 1), (5, 0, 0), (4, 0, 1)]
+
+
+def _grade_combinations(n_grades):
+    import itertools
+    for r in range(n_grades):
+        for grades in itertools.combinations(range(n_grades), r + 1):
+            yield list(grades)
+
+
+@pytest.mark.parametrize('descr,where', _params(ROOTS, [(2, 0, 1)]))
+def test_study_sqrt(descr, where):
+    """test_roots.py:11-38: square roots of the Study numbers x ~x for every grade combination."""
+    rng = np.random.RandomState(5)
+    with _context(descr, where) as ga:
+        hit = 0
+        for grades in _grade_combinations(ga.algebra.n_dimensions + 1):
+            x = random_subspace(ga, ga.subspace.from_grades(grades), (10,), rng).symmetric_reverse_product()
+            if x.subspace.is_study:
+                assert_close(x.square_root().squared(), x)
+                hit += 1
+        assert hit > 0
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_object_square_root(where):
+    """test_roots.py:41-53."""
+    rng = np.random.RandomState(6)
+    with _context((2, 0, 0), where) as ga:
+        v = random_subspace(ga, ga.subspace.bivector(), (10,), rng)
+        assert_close(v.square_root().squared(), v)
+    with _context((0, 2, 0), where) as ga:
+        v = random_subspace(ga, ga.subspace.vector(), (10,), rng)
+        assert_close(v.square_root().squared(), v)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_motor_roots(where):
+    """test_roots.py:56-67."""
+    rng = np.random.RandomState(0)
+    with _context((3, 0, 1), where) as ga:
+        m = random_motor(ga, (10,), rng)
+        assert_close(m.motor_square_root().squared(), m)
+        m = m.select.bivector().degenerate() + 1        # translators
+        assert_close(m.motor_square_root().squared(), m)
+        assert_close(m.motor_geometric_mean(m), m)
+
+
+INVERSE = [(1, 0, 0), (0, 1, 0), (2, 0, 0), (1, 1, 0), (0, 2, 0), (3, 0, 0), (2, 1, 0), (1, 2, 0), (4, 0, 0), (3, 1, 0),
+           (2, 2, 0), (5, 0, 0), (4, 1, 0), (3, 2, 0)]
+
+
+@pytest.mark.parametrize('descr,where', _params(INVERSE, [(3, 0, 0), (2, 1, 0)]))
+def test_inverse_exhaustive(descr, where):
+    """test_inverse.py:10-39: general inversion of every grade combination in dimension < 6, atol 1e-11."""
+    rng = np.random.RandomState(0)
+    with _context(descr, where) as ga:
+        for grades in _grade_combinations(ga.algebra.n_dimensions + 1):
+            x = random_subspace(ga, ga.subspace.from_grades(grades), (10,), rng)
+            i = x.inverse()
+            assert_close(x * i, 1, atol=1e-11)
+            assert_close(i * x, 1, atol=1e-11)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_inverse_simplification_failure(where):
+    """test_inverse.py:42-66 (the part that concerns values)."""
+    rng = np.random.RandomState(7)
+    with _context((5, 0, 0), where) as ga:
+        V = ga.subspace.from_grades([1, 2, 5])
+        assert V.simplicity == 3
+        x = random_subspace(ga, V, (1,), rng)
+        i = x.inverse()
+        assert_close(x * i, 1)
+        assert_close(i * x, 1)
+        z = x.symmetric_reverse_product().symmetric_pseudoscalar_negation_product()
+        assert z.subspace == ga.subspace.from_grades([0, 5])
+        assert ga.compile_only or np.allclose(values_of(z.select[5]), 0)
+
+
+# (function, parameter list) of every GPU-tier identity test: prewarm compiles their kernels at build time
+GPU_MATRIX = [(test_bisect, LOGEXP), (test_study, STUDY), (test_invariant_decomposition, INVARIANT),
+              (test_motor_decompose_euclidean, [(1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1)]), (test_motor_split, SPLIT),
+              (test_study_sqrt, ROOTS), (test_inverse_exhaustive, INVERSE)]
+GPU_SINGLES = [test_object_square_root, test_motor_roots, test_inverse_simplification_failure]
