@@ -474,3 +474,107 @@ def lower_dense(trace: Trace, kernel, kshape, mask, inputs):
             acc = zero
         out.append(acc)
     return out
+
+
+# ---- reverse-mode differentiation of a program -----------------------------------------------------------------
+def build_vjp(ir, np_dtype, faithful=False):
+    """Vector-Jacobian product of a straight-line program as ANOTHER straight-line program (one kernel):
+
+        inputs   the original inputs (same addressing modes), then one cotangent operand per original output
+        outputs  one operand per original input: sum_o cotangent[o] * d out[o] / d input   (per batch item)
+
+    The forward values are recomputed inside the backward kernel (registers are cheaper than HBM: nothing is saved
+    between the passes), then the adjoints are accumulated in reverse program order.  A multilinear operator's
+    backward is thus the same integer table contracted on another axis (numga/operator/operator.py:59-65
+    `swapaxes`, numga/backend/jax/operator.py:128-139), and the non-linear chains (exp, log, normalized ...) get
+    their exact derivative.  Scalar launch parameters are treated as constants."""
+    t = Trace(np_dtype, faithful=faithful)
+    n_in = len(ir['in_width'])
+    in_regs = [t.add_input(w, m if m != rt.INDEXED else rt.VARYING) for w, m in zip(ir['in_width'], ir['in_mode'])]
+    params = [t.add_param() for _ in range(ir['n_params'])]
+    cot_regs = [t.add_input(w, rt.VARYING) for w in ir['out_width']]
+    # forward replay
+    new = []
+    for op, a, b, c in ir['instr']:
+        if op == rt.OP_INPUT:
+            v = in_regs[a][b]
+        elif op == rt.OP_CONST:
+            v = t.const(ir['consts'][a])
+        elif op == rt.OP_PARAM:
+            v = params[a]
+        elif op == rt.OP_ADD: v = t.add(new[a], new[b])
+        elif op == rt.OP_SUB: v = t.sub(new[a], new[b])
+        elif op == rt.OP_MUL: v = t.mul(new[a], new[b])
+        elif op == rt.OP_DIV: v = t.div(new[a], new[b])
+        elif op == rt.OP_NEG: v = t.neg(new[a])
+        elif op == rt.OP_SQRT: v = t.sqrt(new[a])
+        elif op == rt.OP_RSQRT: v = t.rsqrt(new[a])
+        elif op == rt.OP_RCP: v = t.rcp(new[a])
+        elif op == rt.OP_ABS: v = t.abs(new[a])
+        elif op == rt.OP_NAN_TO_NUM: v = t._emit(op, new[a], new[b])
+        elif op in (rt.OP_FMA, rt.OP_SELECT_GT0): v = t._emit(op, new[a], new[b], new[c])
+        elif op in (rt.OP_MIN, rt.OP_MAX): v = t._emit(op, new[a], new[b])
+        else: v = t._emit(op, new[a])          # exp, log, sin, cos
+        new.append(v)
+    # reverse sweep
+    adj = {}
+
+    def acc(v, g):
+        if t.const_value(v) is not None:
+            return
+        adj[v] = g if v not in adj else t.add(adj[v], g)
+    for k, c, v in ir['stores']:
+        acc(new[v], cot_regs[k][c])
+    zero, half = t.const(0.0), t.const(0.5)
+    # adjoints are keyed by NEW ids (hash-consing can merge old values); walk old instructions backwards, visiting
+    # every new id once, at its last defining old instruction
+    seen = set()
+    for old in range(len(ir['instr']) - 1, -1, -1):
+        v = new[old]
+        if v in seen or v not in adj:
+            continue
+        seen.add(v)
+        op, a, b, c = t.instr[v]
+        g = adj[v]
+        if op in (rt.OP_INPUT, rt.OP_CONST, rt.OP_PARAM):
+            continue
+        if op == rt.OP_ADD:
+            acc(a, g); acc(b, g)
+        elif op == rt.OP_SUB:
+            acc(a, g); acc(b, t.neg(g))
+        elif op == rt.OP_MUL:
+            acc(a, t.mul(g, b)); acc(b, t.mul(g, a))
+        elif op == rt.OP_DIV:
+            q = t.div(g, b)
+            acc(a, q); acc(b, t.neg(t.mul(q, v)))
+        elif op == rt.OP_NEG:
+            acc(a, t.neg(g))
+        elif op == rt.OP_SQRT:
+            acc(a, t.mul(t.mul(g, half), t.rcp(v)))
+        elif op == rt.OP_RSQRT:
+            acc(a, t.neg(t.mul(t.mul(g, half), t.mul(v, t.mul(v, v)))))
+        elif op == rt.OP_RCP:
+            acc(a, t.neg(t.mul(g, t.mul(v, v))))
+        elif op == rt.OP_ABS:
+            acc(a, t._emit(rt.OP_SELECT_GT0, a, g, t.neg(g)))
+        elif op == rt.OP_NAN_TO_NUM:
+            acc(a, g)
+        elif op == rt.OP_FMA:
+            acc(a, t.mul(g, b)); acc(b, t.mul(g, a)); acc(c, g)
+        elif op == rt.OP_EXP:
+            acc(a, t.mul(g, v))
+        elif op == rt.OP_LOG:
+            acc(a, t.div(g, a))
+        elif op == rt.OP_SIN:
+            acc(a, t.mul(g, t._emit(rt.OP_COS, a)))
+        elif op == rt.OP_COS:
+            acc(a, t.neg(t.mul(g, t._emit(rt.OP_SIN, a))))
+        elif op in (rt.OP_MIN, rt.OP_MAX):
+            d = t.sub(b, a) if op == rt.OP_MIN else t.sub(a, b)       # > 0: a is selected
+            acc(a, t._emit(rt.OP_SELECT_GT0, d, g, zero)); acc(b, t._emit(rt.OP_SELECT_GT0, d, zero, g))
+        elif op == rt.OP_SELECT_GT0:
+            acc(b, t._emit(rt.OP_SELECT_GT0, a, g, zero)); acc(c, t._emit(rt.OP_SELECT_GT0, a, zero, g))
+        else:
+            raise NotImplementedError(f'derivative of opcode {op}')
+    outputs = [[adj.get(r, zero) for r in regs] for regs in in_regs]
+    return t.finish(outputs)

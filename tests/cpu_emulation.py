@@ -2,7 +2,7 @@
 numpy IR interpreter (tests/ir_interp.py).
 
 The product (numga_b200/) has no CPU execution path and no hook for one; this module monkeypatches
-`CompiledFunction.__call__` / `B200Operator.__call__` from the outside, inside a context manager, so that the CPU
+`CompiledFunction.launch` / `B200Operator.__call__` from the outside, inside a context manager, so that the CPU
 test tier can check orchestration logic numerically (broadcasting, gather/scatter, the physics step) against golden
 data without a GPU.  The arithmetic is that of the IR, op by op in the context dtype (= FAITHFUL semantics).
 """
@@ -18,7 +18,7 @@ from numga_b200 import runtime as rt
 
 @contextlib.contextmanager
 def emulate_launches():
-    orig_call, orig_op_call = B.CompiledFunction.__call__, B.B200Operator.__call__
+    orig_call, orig_op_call = B.CompiledFunction.launch, B.B200Operator.__call__
 
     def compiled_call(self, args, bshape=None, out=None):
         ctx = self.context
@@ -60,11 +60,11 @@ def emulate_launches():
             return orig_op_call(self, *inputs)
         return self.context.engine.call(('operator', id(self.operator)), lambda *xs: orig_op_call(self, *xs), inputs)
 
-    B.CompiledFunction.__call__, B.B200Operator.__call__ = compiled_call, operator_call
+    B.CompiledFunction.launch, B.B200Operator.__call__ = compiled_call, operator_call
     try:
         yield
     finally:
-        B.CompiledFunction.__call__, B.B200Operator.__call__ = orig_call, orig_op_call
+        B.CompiledFunction.launch, B.B200Operator.__call__ = orig_call, orig_op_call
 
 
 def emulated_context(algebra, dtype=torch.float64, mode='faithful'):
