@@ -183,6 +183,25 @@ def device_mv(ctx, sub, n, seed, rank, scale=1.0):
     return ctx.multivector(values=v, subspace=sub)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the page-locked staging buffers of the
+    host path are allocated (first touch) on the NUMA node the GPU's PCIe root hangs off.  Returns the CPU count or
+    None when NVML / affinity is unavailable (the run is still valid, just not NUMA-local)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def time_steps(fn, steps, warmup, dist=None):
     """CUDA-event timing on the launching stream, barrier + synchronize on both sides, max over ranks."""
     import torch
@@ -380,6 +399,8 @@ def run_ours(args):
 
     # ---- end to end through the C-ABI host-buffer call ---------------------------------------------------------
     import ctypes
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)      # pinned host buffers are first touched on the GPU's own NUMA node
     prog = ctx.engine.cache[next(k for k in ctx.engine.cache if k[0][0] == 'jit')].program
     e2e_n = n
     try:
@@ -417,9 +438,11 @@ def run_ours(args):
     e2e_ok = bool(np.array_equal(check, host_q[:, :1 << 16]))
     e2e = {'value': world * e2e_n / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': 16 * e2e_n + 32,
            'd2h_bytes_per_step': 16 * e2e_n, 'steps': e2e_steps, 'points_per_gpu': e2e_n,
-           'matches_device_result': e2e_ok, 'path': 'ngb200_program_run_host (pinned host SoA buffers, chunked H2D/kernel/D2H over 4 streams)'}
+           'matches_device_result': e2e_ok, 'numa_local_cpus': numa,
+           'path': 'ngb200_program_run_host (pinned host SoA buffers, 128 MB chunks, H2D/kernel/D2H pipelined over 4 streams)'}
     for h in (hin, hout, hR):
         rt.lib.ngb200_host_free(h)
+    os.sched_setaffinity(0, all_cpus)        # the CPU baseline below gets every host core back
 
     # ---- optional final gather over NVLink (not on the hot path; timed separately) ------------------------------
     gather = None
