@@ -23,6 +23,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -237,10 +238,13 @@ struct Gen {
     std::vector<int> yoff;    // offset of each output in y[]
     int NX = 0, NU = 0, NY = 0;
     int max_live = 0;         // peak number of simultaneously live per-item values (see analyse)
+    std::vector<int> order;   // emission order of the varying, non-input values of the body
+    bool faithful_order = true;    // true: emit in IR order; false: input-frontier order (see analyse)
 
     explicit Gen(const ngb200_program &p)
         : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {
         approx = !f64 && !faithful && !env_int("NGB200_PRECISE_MATH", 0);
+        faithful_order = env_int("NGB200_IR_ORDER", 1) != 0;
     }
 
     // name of value v as seen from uniform (preamble) or varying (body) code
@@ -455,31 +459,6 @@ struct Gen {
             for (int j = 0; j < k; ++j) want_slot(ops[j]);
         }
         for (const ngb200_store &s : P.stores) want_slot(s.value);
-        // register demand: the largest number of per-item values alive at once when the program runs in IR order
-        // (inputs become live at their first use, stored values stay live to the end)
-        {
-            std::vector<int> first_use(n, -1), last_use(n, -1), delta(n + 2, 0);
-            for (int v = 0; v < n; ++v) {
-                if (!live[v]) continue;
-                const ngb200_instr &I = P.instr[v];
-                const int k = n_operands_of(I.op);
-                const int ops[3] = {I.a, I.b, I.c};
-                for (int j = 0; j < k; ++j) {
-                    if (first_use[ops[j]] < 0) first_use[ops[j]] = v;
-                    last_use[ops[j]] = v;
-                }
-            }
-            for (const ngb200_store &s : P.stores) last_use[s.value] = n;
-            for (int v = 0; v < n; ++v) {
-                if (!live[v] || uniform[v] || last_use[v] < 0) continue;
-                const int start = P.instr[v].op == NGB200_OP_INPUT ? (first_use[v] < 0 ? n : first_use[v]) : v;
-                delta[start] += 1;
-                delta[last_use[v]] -= 1;
-            }
-            int cur = 0;
-            max_live = 0;
-            for (int v = 0; v <= n; ++v) { cur += delta[v]; if (cur > max_live) max_live = cur; }
-        }
         xoff.assign(P.in_width.size(), 0);
         for (size_t k = 0; k < P.in_width.size(); ++k) {
             xoff[k] = NX;
@@ -487,6 +466,54 @@ struct Gen {
         }
         yoff.assign(P.out_width.size(), 0);
         for (size_t k = 0; k < P.out_width.size(); ++k) { yoff[k] = NY; NY += P.out_width[k]; }
+        // Emission order of the per-item body: stable sort by "input frontier" = the last input component (in load
+        // order) a value depends on.  A bilinear form whose chains are summed in the order of one operand thereby
+        // becomes INPUT-major: all accumulators advance as each component of that operand arrives, so the loads of
+        // a thread overlap with its arithmetic and only one operand has to be resident in registers (CGA full x
+        // full: output-major 123 registers and every FMA chain waits for all 64 loads).  Dependent values never
+        // have a smaller frontier than their operands, so the order stays topological.
+        {
+            std::vector<int> frontier(n, -1);
+            for (int v = 0; v < n; ++v) {
+                if (!live[v] || uniform[v]) continue;
+                const ngb200_instr &I = P.instr[v];
+                if (I.op == NGB200_OP_INPUT) { frontier[v] = xoff[I.a] + I.b; continue; }
+                const int k = n_operands_of(I.op);
+                const int ops[3] = {I.a, I.b, I.c};
+                for (int j = 0; j < k; ++j) if (frontier[ops[j]] > frontier[v]) frontier[v] = frontier[ops[j]];
+            }
+            order.clear();
+            for (int v = 0; v < n; ++v)
+                if (live[v] && !uniform[v] && P.instr[v].op != NGB200_OP_INPUT) order.push_back(v);
+            if (!faithful_order)
+                std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return frontier[l] < frontier[r]; });
+        }
+        // register demand: the largest number of per-item values alive at once when the body runs in that order
+        // (inputs become live at their first use, stored values stay live to the end)
+        {
+            const int m = (int)order.size();
+            std::vector<int> pos(n, -1), first_use(n, -1), last_use(n, -1), delta(m + 2, 0);
+            for (int q = 0; q < m; ++q) pos[order[q]] = q;
+            for (int q = 0; q < m; ++q) {
+                const ngb200_instr &I = P.instr[order[q]];
+                const int k = n_operands_of(I.op);
+                const int ops[3] = {I.a, I.b, I.c};
+                for (int j = 0; j < k; ++j) {
+                    if (first_use[ops[j]] < 0) first_use[ops[j]] = q;
+                    last_use[ops[j]] = q;
+                }
+            }
+            for (const ngb200_store &st : P.stores) last_use[st.value] = m;
+            for (int v = 0; v < n; ++v) {
+                if (!live[v] || uniform[v] || last_use[v] < 0) continue;
+                const int start = P.instr[v].op == NGB200_OP_INPUT ? (first_use[v] < 0 ? m : first_use[v]) : pos[v];
+                delta[start] += 1;
+                delta[last_use[v]] -= 1;
+            }
+            int cur = 0;
+            max_live = 0;
+            for (int q = 0; q <= m; ++q) { cur += delta[q]; if (cur > max_live) max_live = cur; }
+        }
         return NGB200_OK;
     }
 
@@ -544,10 +571,7 @@ struct Gen {
         // ---- per-item body ----------------------------------------------------------------
         appendf(s, "__device__ __forceinline__ void ngb_body(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
                 NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
-        for (int v = 0; v < n; ++v) {
-            if (!live[v] || uniform[v]) continue;
-            const ngb200_instr &I = P.instr[v];
-            if (I.op == NGB200_OP_INPUT) continue;
+        for (int v : order) {
             ++nl;
             if (fused_into[v] >= 0) continue;      // this multiply lives inside the FMA of its consumer
             appendf(s, "  const T r%d = %s;\n", v, expr(v, true).c_str());
@@ -568,9 +592,8 @@ struct Gen {
             s += "__device__ __forceinline__ float2 ngb_neg2(float2 a) { return make_float2(-a.x, -a.y); }\n";
             appendf(s, "__device__ __forceinline__ void ngb_body2(const float2 (&x)[%d], const T (&u)[%d], float2 (&y)[%d]) {\n",
                     NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
-            for (int v = 0; v < n; ++v) {
-                if (!live[v] || uniform[v] || fused_into[v] >= 0) continue;
-                if (P.instr[v].op == NGB200_OP_INPUT) continue;
+            for (int v : order) {
+                if (fused_into[v] >= 0) continue;
                 appendf(s, "  const float2 r%d = %s;\n", v, expr2(v).c_str());
             }
             for (int j = 0; j < NY; ++j) {
@@ -724,12 +747,12 @@ static void write_file(const std::string &path, const char *data, size_t n) {
     rename(tmp.c_str(), path.c_str());
 }
 
-static int nvrtc_compile(const std::string &src, std::vector<char> &cubin) {
+static int nvrtc_compile(const std::string &src, std::vector<char> &cubin, std::string *log_out = nullptr) {
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, src.c_str(), "ngb200_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(NGB200_ERR_COMPILE, "nvrtcCreateProgram failed");
     const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--fmad=true",
-                          "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
+                          "--prec-div=true", "--prec-sqrt=true", "--ftz=false", "--ptxas-options=-v"};
     nvrtcResult r = nvrtcCompileProgram(prog, (int)(sizeof opts / sizeof *opts), opts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
@@ -739,6 +762,12 @@ static int nvrtc_compile(const std::string &src, std::vector<char> &cubin) {
         nvrtcDestroyProgram(&prog);
         return fail(NGB200_ERR_COMPILE, "NVRTC: %s\n%.3000s", nvrtcGetErrorString(r), log.c_str());
     }
+    if (log_out) {
+        size_t ln = 0;
+        nvrtcGetProgramLogSize(prog, &ln);
+        log_out->assign(ln, 0);
+        if (ln) nvrtcGetProgramLog(prog, &(*log_out)[0]);
+    }
     size_t n = 0;
     nvrtcGetCUBINSize(prog, &n);
     cubin.resize(n);
@@ -746,6 +775,16 @@ static int nvrtc_compile(const std::string &src, std::vector<char> &cubin) {
     nvrtcDestroyProgram(&prog);
     if (n == 0) return fail(NGB200_ERR_COMPILE, "NVRTC produced no cubin");
     return NGB200_OK;
+}
+
+// bytes of spill stores ptxas reports for one entry function in a `-v` log (0 if the function is not listed)
+static long spill_bytes(const std::string &log, const char *entry) {
+    size_t at = log.find(std::string("entry function '") + entry + "'");
+    if (at == std::string::npos) return 0;
+    size_t sp = log.find("bytes spill stores", at);
+    if (sp == std::string::npos) return 0;
+    size_t b = log.rfind(',', sp);
+    return b == std::string::npos ? 0 : atol(log.c_str() + b + 1);
 }
 
 static int env_int(const char *name, int dflt) {
@@ -785,32 +824,80 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     // from the program's own peak number of live values; small (HBM-bound) programs keep ptxas' natural choice.
     // Programs that need more than 128 registers run 128-thread CTAs: finer occupancy granularity (CGA full x full,
     // 2 items/thread: 168 registers -> 3 CTAs of 128 instead of 1 CTA of 256, 4.33 vs 5.86 ms).
-    P->minb = 1;
-    P->tpb = 256;
-    if (live_guess >= 256) {
-        const int need = gen.max_live * (f32 ? 1 : 2) * vec + 16;
-        if (need > 128) P->tpb = 128;
-        int minb = 65536 / (P->tpb * need);
-        P->minb = minb < 1 ? 1 : (minb > 8 ? 8 : minb);
-    }
-    if (env_int("NGB200_TPB", 0) > 0) P->tpb = env_int("NGB200_TPB", 0);
-    if (env_int("NGB200_MINBLOCKS", 0) > 0) P->minb = env_int("NGB200_MINBLOCKS", 0);
-    P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform, pair);
+    auto make_variant = [&](bool ir_order) {
+        if (gen.faithful_order != ir_order) {
+            gen.faithful_order = ir_order;
+            gen.NX = gen.NU = gen.NY = 0;
+            gen.analyse();
+        }
+        P->minb = 1;
+        P->tpb = 256;
+        if (live_guess >= 256) {
+            const int need = gen.max_live * (f32 ? 1 : 2) * vec + 16;
+            if (need > 128) P->tpb = 128;
+            int minb = 65536 / (P->tpb * need);
+            P->minb = minb < 1 ? 1 : (minb > 8 ? 8 : minb);
+        }
+        if (env_int("NGB200_TPB", 0) > 0) P->tpb = env_int("NGB200_TPB", 0);
+        if (env_int("NGB200_MINBLOCKS", 0) > 0) P->minb = env_int("NGB200_MINBLOCKS", 0);
+        P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform, pair);
+        P->hash = hash_hex(P->source + "|sm_100a");
+    };
     P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
     if (P->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel (%zu parameter bytes)", P->param_bytes);
 
-    // the key is the generated source alone: a cubin built at build() time by this image's NVRTC stays
-    // valid when torch's bundled (older) libnvrtc happens to be the one loaded in the process
-    P->hash = hash_hex(P->source + "|sm_100a");
+    // Two emission orders of the same program (Gen::analyse): IR order, and input-frontier order.  Which one ptxas
+    // turns into the better kernel depends on the program (frontier order removes the spills of the fp64 gathered
+    // physics kernels, -17 % time; it costs the flat CGA product 10 %), so the choice is made on ptxas' own report:
+    // IR order unless it spills, then whichever spills less.  The cache key is the generated source alone: a cubin
+    // built at build() time by this image's NVRTC stays valid when torch's bundled (older) libnvrtc happens to be
+    // the one loaded in the process; `<hash>.alt` marks "the other order won" for the IR-order hash.
+    const int forced = env_int("NGB200_IR_ORDER", -1);
+    make_variant(forced != 0);
     std::lock_guard<std::mutex> lock(g_mu);
+    const bool use_cache = !env_int("NGB200_NO_CACHE", 0);
     std::string base = cache_dir() + "/" + P->hash;
-    if (!env_int("NGB200_NO_CACHE", 0) && read_file(base + ".cubin", P->cubin)) {
+    if (use_cache && read_file(base + ".cubin", P->cubin)) {
         P->cache_hit = true;
         return NGB200_OK;
     }
-    rc = nvrtc_compile(P->source, P->cubin);
+    std::vector<char> marker;
+    if (forced < 0 && use_cache && read_file(base + ".alt", marker)) {
+        make_variant(false);
+        base = cache_dir() + "/" + P->hash;
+        if (read_file(base + ".cubin", P->cubin)) {
+            P->cache_hit = true;
+            return NGB200_OK;
+        }
+        rc = nvrtc_compile(P->source, P->cubin);
+        if (rc) return rc;
+        write_file(base + ".cubin", P->cubin.data(), P->cubin.size());
+        write_file(base + ".cu", P->source.data(), P->source.size());
+        return NGB200_OK;
+    }
+    std::string log;
+    rc = nvrtc_compile(P->source, P->cubin, &log);
     if (rc) return rc;
+    const char *main_kernel = vec > 1 ? "ngb_vec" : "ngb_scalar";
+    const long spill_ir = spill_bytes(log, main_kernel);
+    if (forced < 0 && spill_ir > 0) {
+        std::string src_ir = P->source, hash_ir = P->hash;
+        std::vector<char> cubin_ir = P->cubin;
+        const int tpb_ir = P->tpb, minb_ir = P->minb, nl = P->n_live, nu = P->n_uniform;
+        make_variant(false);
+        std::vector<char> cubin_alt;
+        std::string log_alt;
+        if (nvrtc_compile(P->source, cubin_alt, &log_alt) == NGB200_OK && spill_bytes(log_alt, main_kernel) < spill_ir) {
+            P->cubin = cubin_alt;
+            base = cache_dir() + "/" + P->hash;
+            write_file((cache_dir() + "/" + hash_ir + ".alt").c_str(), P->hash.data(), P->hash.size());
+        } else {
+            make_variant(true);          // restore the IR-order program
+            P->cubin = cubin_ir;
+            P->tpb = tpb_ir; P->minb = minb_ir; P->n_live = nl; P->n_uniform = nu;
+        }
+    }
     write_file(base + ".cubin", P->cubin.data(), P->cubin.size());
     write_file(base + ".cu", P->source.data(), P->source.size());
     return NGB200_OK;
@@ -929,9 +1016,14 @@ extern "C" int ngb200_operator_create(const int32_t *terms, int32_t n_terms, int
                 acc = acc < 0 ? prod : B.emit(NGB200_OP_ADD, acc, prod);
             }
         } else {
-            for (int t = 0; t < n_terms; ++t) {
+            // FAST: sum each output in the order of the LAST operand's component, so that the input-frontier emission
+            // order (Gen::analyse) streams that operand; FAITHFUL keeps precompute_sparse order (= einsum's)
+            std::vector<int> row;
+            for (int t = 0; t < n_terms; ++t) if (terms[t * w + arity] == o) row.push_back(t);
+            if (!faithful)
+                std::stable_sort(row.begin(), row.end(), [&](int l, int r) { return terms[l * w + arity - 1] < terms[r * w + arity - 1]; });
+            for (int t : row) {
                 const int32_t *term = terms + t * w;
-                if (term[arity] != o) continue;
                 int c = term[arity + 1];
                 int prod = signed_product(term, true, true, c == -1 ? 1 : c);
                 if (acc < 0) acc = c == -1 ? B.emit(NGB200_OP_NEG, prod) : prod;

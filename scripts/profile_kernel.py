@@ -52,7 +52,7 @@ if which in ('cga_time', 'roundtrip_time'):
     import time
     from bench import time_steps
     if which == 'cga_time':
-        ctx = B200Context((4, 1, 0)); F = ctx.subspace.full(); n = 1 << 26
+        ctx = B200Context((4, 1, 0)); F = ctx.subspace.full(); n = 1 << int(os.environ.get('LOGN', '26'))
         a, b = device_mv(ctx, F, n, 5, 0), device_mv(ctx, F, n, 6, 0)
         run = lambda: a * b; bpi = 384
     else:
