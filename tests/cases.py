@@ -61,6 +61,15 @@ CASES = [
     ('cga3_gp_even', CGA3, [('even_grade', B), ('even_grade', B)], 1.0, lambda a, b: a * b),
     ('cga3_sandwich_vector', CGA3, [('even_grade', B), ('vector', B)], 1.0, lambda r, v: r >> v),
     ('cga3_exp', CGA3, [('bivector', B)], 0.3, lambda b: b.exp()),
+    # --- decompositions (extension/decompose.py) ------------------------------------------------------------------------------------
+    ('pga3_decompose_invariant_l', PGA3, [('bivector', B)], 0.7, lambda b: b.decompose_invariant()[0]),
+    ('pga3_decompose_invariant_r', PGA3, [('bivector', B)], 0.7, lambda b: b.decompose_invariant()[1]),
+    ('pga3_motor_translator', PGA3, [('even_grade', B)], 1.0, lambda m: m.motor_translator()),
+    ('pga3_motor_rotor', PGA3, [('even_grade', B)], 1.0, lambda m: m.motor_rotor()),
+    ('pga3_motor_split_t', PGA3, [('bivector', B), ('antivector', B)], 0.5, lambda b, o: b.exp().motor_split(o)[0]),
+    ('pga3_motor_split_r', PGA3, [('bivector', B), ('antivector', B)], 0.5, lambda b, o: b.exp().motor_split(o)[1]),
+    ('cga3_decompose_invariant_l', CGA3, [('bivector', B)], 0.5, lambda b: b.decompose_invariant()[0]),
+    ('vga3_decompose_invariant_l', VGA3, [('bivector', B)], 0.5, lambda b: b.decompose_invariant()[0]),
     # --- other signatures ------------------------------------------------------------------------------------------------------------
     ('sta_gp_full', STA, [('multivector', B), ('multivector', B)], 1.0, lambda a, b: a * b),
     ('sta_exp_log', STA, [('bivector', B)], 0.3, lambda b: b.exp().motor_log()),

@@ -27,7 +27,8 @@ TOL = {np.float32: 1e-5, np.float64: 1e-12}
 CHAIN_TOL = {np.float32: 2e-3, np.float64: 1e-9}
 ILL_CONDITIONED = ('exp', 'log', 'roundtrip', 'motor_sqrt')
 NOT_BIT_REPRODUCIBLE = {'pga3_sandwich_point_bcast', 'pga3_normalize_then_apply', 'pga3_normalized_vector',
-                        'vga3_rotor_roundtrip', 'pga2_exp_log', 'pga2_normalized'}
+                        'vga3_rotor_roundtrip', 'pga2_exp_log', 'pga2_normalized',
+                        'pga3_motor_split_t', 'pga3_motor_split_r'}    # (m >> o) / o + 1 normalizes through x ** -0.5
 
 
 def _ctx(pqr, dtype, mode='fast'):
