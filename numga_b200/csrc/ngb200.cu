@@ -67,7 +67,7 @@ extern "C" int64_t ngb200_launch_count(void) { return g_launches.load(); }
 #define DRV_FUNCS(X)                                                                              \
     X(cuInit) X(cuGetErrorString) X(cuCtxGetCurrent) X(cuCtxSetCurrent) X(cuCtxGetDevice)         \
     X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData)        \
-    X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute)                                \
+    X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute) X(cuFuncSetAttribute)                                \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemAlloc) X(cuMemFree)                     \
     X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuStreamCreate)                \
     X(cuStreamSynchronize) X(cuStreamDestroy) X(cuMemAllocHost) X(cuMemFreeHost)
@@ -150,9 +150,9 @@ static const int kMaxDevices = 32;
 struct Loaded {
     std::atomic<int> ready{0};
     CUmodule mod = nullptr;
-    CUfunction fvec = nullptr, fscalar = nullptr;
-    int regs_vec = 0, regs_scalar = 0;
-    int grid_vec = 0, grid_scalar = 0;  // persistent grid sizes (SMs x resident CTAs)
+    CUfunction fvec = nullptr, fscalar = nullptr, fstage = nullptr;
+    int regs_vec = 0, regs_scalar = 0, regs_stage = 0;
+    int grid_vec = 0, grid_scalar = 0, grid_stage = 0;  // persistent grid sizes (SMs x resident CTAs)
 };
 
 struct ngb200_program {
@@ -166,6 +166,9 @@ struct ngb200_program {
     int vec = 1;          // items per thread in the vector kernel (1 = no vector kernel)
     int tpb = 256;
     int minb = 1;         // __launch_bounds__ min resident CTAs per SM (caps registers at 65536 / (tpb * minb))
+    // staged kernel (bulk async copies global -> shared, mbarrier pipeline); 0 = not generated
+    int stage_tpb = 0, stage_stages = 0, stage_nx = 0;
+    size_t stage_smem = 0;
     int n_live = 0, n_uniform = 0;
     bool cache_hit = false;
     std::string source, hash;
@@ -680,6 +683,65 @@ struct Gen {
                 }
             s += "  }\n}\n";
         }
+        // ---- staged kernel: TMA-style bulk copies global -> shared, mbarrier full-barriers, S-deep pipeline -----
+        // One elected thread per CTA issues one `cp.async.bulk` per input component row of the NEXT tiles while all
+        // threads compute the current tile out of shared memory: the loads of a register-heavy kernel no longer
+        // depend on how many warps fit (CGA full x full: 12 warps/SM, top stall long_scoreboard).  Outputs go
+        // straight to global memory (coalesced, written once).
+        if (P.stage_tpb > 0) {
+            const int TP = P.stage_tpb, S = P.stage_stages;
+            const int es = f64 ? 8 : 4;
+            appendf(s, "#define NGB_STP %d\n#define NGB_SS %d\n", TP, S);
+            s += "__device__ __forceinline__ unsigned ngb_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }\n";
+            s += "__device__ __forceinline__ void ngb_mbar_wait(unsigned bar, unsigned phase) {\n"
+                 "  asm volatile(\"{\\n.reg .pred p;\\nNGB_WAIT:\\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\\n@p bra NGB_DONE;\\nbra NGB_WAIT;\\nNGB_DONE:\\n}\" :: \"r\"(bar), \"r\"(phase) : \"memory\");\n}\n";
+            s += "__device__ __forceinline__ void ngb_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {\n"
+                 "  asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" :: \"r\"(dst), \"l\"(src), \"r\"(bytes), \"r\"(bar) : \"memory\");\n}\n";
+            // issue all rows of tile t into stage st
+            s += "__device__ __forceinline__ void ngb_issue(const Params& p, T* buf, unsigned bar, int st, long long t) {\n";
+            appendf(s, "  asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%%0], %%1;\" :: \"r\"(bar), \"r\"(%uu) : \"memory\");\n",
+                    (unsigned)(NX * TP * es));
+            for (int k = 0; k < nin; ++k) {
+                if (P.in_mode[k] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < P.in_width[k]; ++c)
+                    appendf(s, "  ngb_bulk(ngb_smem(buf + ((long long)st * %d + %d) * NGB_STP), p.in[%d].ptr + %dLL * p.in[%d].cs + t * NGB_STP, %uu, bar);\n",
+                            NX, xoff[k] + c, k, c, k, (unsigned)(TP * es));
+            }
+            s += "}\n";
+            int cta_per_sm = (int)(232448 / ((size_t)S * NX * TP * es + 1024));     // what shared memory allows
+            if (cta_per_sm < 1) cta_per_sm = 1;
+            if (cta_per_sm > 8) cta_per_sm = 8;
+            appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_STP, %d) ngb_stage(const Params p) {\n", cta_per_sm);
+            s += "  extern __shared__ __align__(128) unsigned char ngb_raw[];\n";
+            s += "  T* buf = reinterpret_cast<T*>(ngb_raw);\n";
+            s += "  __shared__ __align__(8) unsigned long long full[NGB_SS];\n";
+            s += "  const int tid = threadIdx.x;\n";
+            s += "  const long long ntiles = p.n / NGB_STP;\n";
+            s += "  if (tid == 0) {\n";
+            s += "    for (int st = 0; st < NGB_SS; ++st) asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" :: \"r\"(ngb_smem(&full[st])));\n";
+            s += "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n";
+            s += "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
+            s += "  }\n  __syncthreads();\n";
+            appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+            s += "  if (tid == 0) {\n    for (int st = 0; st < NGB_SS; ++st) {\n      const long long t = (long long)blockIdx.x + (long long)st * gridDim.x;\n"
+                 "      if (t < ntiles) ngb_issue(p, buf, ngb_smem(&full[st]), st, t);\n    }\n  }\n";
+            s += "  int it = 0;\n";
+            s += "  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {\n";
+            s += "    const int st = it % NGB_SS;\n";
+            s += "    ngb_mbar_wait(ngb_smem(&full[st]), (unsigned)((it / NGB_SS) & 1));\n";
+            appendf(s, "    T x[%d]; T y[%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
+            appendf(s, "    const T* tile = buf + (long long)st * %d * NGB_STP + tid;\n", NX);
+            for (int j = 0; j < NX; ++j) appendf(s, "    x[%d] = tile[%d * NGB_STP];\n", j, j);
+            s += "    ngb_body(x, u, y);\n";
+            s += "    const long long i = t * NGB_STP + tid;\n";
+            for (int k = 0; k < nout; ++k)
+                for (int c = 0; c < P.out_width[k]; ++c)
+                    appendf(s, "    NGB_ST(p.out[%d].ptr + %dLL * p.out[%d].cs + i, y[%d]);\n", k, c, k, yoff[k] + c);
+            s += "    __syncthreads();\n";      // every thread has read stage st: it can be refilled
+            s += "    if (tid == 0) {\n      const long long nt = t + (long long)NGB_SS * gridDim.x;\n"
+                 "      if (nt < ntiles) ngb_issue(p, buf, ngb_smem(&full[st]), st, nt);\n    }\n";
+            s += "  }\n}\n";
+        }
         return s;
     }
 };
@@ -824,6 +886,12 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     // from the program's own peak number of live values; small (HBM-bound) programs keep ptxas' natural choice.
     // Programs that need more than 128 registers run 128-thread CTAs: finer occupancy granularity (CGA full x full,
     // 2 items/thread: 168 registers -> 3 CTAs of 128 instead of 1 CTA of 256, 4.33 vs 5.86 ms).
+    // staged kernel: experimental knob NGB200_STAGE=1 (wide, non-gathered programs only)
+    P->stage_tpb = 0;
+    if (env_int("NGB200_STAGE", 0) && !P->any_indexed && gen.NX > 0) {
+        P->stage_tpb = env_int("NGB200_STAGE_TPB", 128);
+        P->stage_stages = env_int("NGB200_STAGES", 2);
+    }
     auto make_variant = [&](bool ir_order) {
         if (gen.faithful_order != ir_order) {
             gen.faithful_order = ir_order;
@@ -842,6 +910,8 @@ static int finish_program(ngb200_program *P, int vec_hint) {
         if (env_int("NGB200_MINBLOCKS", 0) > 0) P->minb = env_int("NGB200_MINBLOCKS", 0);
         P->source = gen.generate(vec, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), &P->n_live, &P->n_uniform, pair);
         P->hash = hash_hex(P->source + "|sm_100a");
+        P->stage_nx = gen.NX;
+        P->stage_smem = (size_t)P->stage_stages * gen.NX * P->stage_tpb * esize(P->dtype);
     };
     P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
@@ -1094,6 +1164,13 @@ static int load_on_device(ngb200_program *P, int dev, Loaded **out) {
                 CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fvec, P->tpb, 0));
                 L.grid_vec = sms * (nb > 0 ? nb : 1) * waves;
             }
+            if (P->stage_tpb > 0) {
+                CU(cuModuleGetFunction(&L.fstage, L.mod, "ngb_stage"));
+                CU(cuFuncGetAttribute(&L.regs_stage, CU_FUNC_ATTRIBUTE_NUM_REGS, L.fstage));
+                CU(cuFuncSetAttribute(L.fstage, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)P->stage_smem));
+                CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fstage, P->stage_tpb, P->stage_smem));
+                L.grid_stage = sms * (nb > 0 ? nb : 1);       // one resident wave: every CTA keeps its pipeline primed
+            }
             L.ready.store(1, std::memory_order_release);
         }
     }
@@ -1108,7 +1185,9 @@ struct DevOperand {
 };
 
 static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t work, const ngb200_operand *in,
-                      const ngb200_operand *out, const double *params, int64_t n, int64_t offset, CUstream stream) {
+                      const ngb200_operand *out, const double *params, int64_t n, int64_t offset, CUstream stream,
+                      int tpb = 0, size_t smem = 0) {
+    if (tpb <= 0) tpb = P->tpb;
     const size_t nin = P->in_width.size(), nout = P->out_width.size();
     const size_t nin_s = nin ? nin : 1, nout_s = nout ? nout : 1, np_s = P->n_params > 0 ? P->n_params : 1;
     std::vector<char> buf(P->param_bytes, 0);
@@ -1129,11 +1208,11 @@ static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t wor
     double *sc = reinterpret_cast<double *>(buf.data() + 32 * (nin_s + nout_s));
     for (int k = 0; k < P->n_params; ++k) sc[k] = params ? params[k] : 0.0;
     *reinterpret_cast<long long *>(buf.data() + 32 * (nin_s + nout_s) + 8 * np_s) = n;
-    int64_t blocks = (work + P->tpb - 1) / P->tpb;
+    int64_t blocks = (work + tpb - 1) / tpb;
     if (blocks > grid_cap) blocks = grid_cap;
     if (blocks < 1) blocks = 1;
     void *args[] = {buf.data()};
-    CU(cuLaunchKernel(f, (unsigned)blocks, 1, 1, (unsigned)P->tpb, 1, 1, 0, stream, args, nullptr));
+    CU(cuLaunchKernel(f, (unsigned)blocks, 1, 1, (unsigned)tpb, 1, 1, (unsigned)smem, stream, args, nullptr));
     g_launches.fetch_add(1);
     return NGB200_OK;
 }
@@ -1172,6 +1251,24 @@ extern "C" int ngb200_program_launch(ngb200_program *P, const ngb200_operand *in
         for (size_t k = 0; k < P->out_width.size() && vec_ok; ++k) vec_ok = aligned(out[k], P->out_width[k]);
     }
     CUstream s = (CUstream)stream;
+    if (P->stage_tpb > 0 && L->fstage && batch >= (int64_t)P->stage_tpb * 4) {
+        // staged kernel: needs batch_stride 1 and 16-byte aligned rows for the bulk copies
+        bool ok = true;
+        const int64_t tile_bytes = (int64_t)P->stage_tpb * es;
+        for (size_t k = 0; k < P->in_width.size() && ok; ++k) {
+            if (P->in_mode[k] != NGB200_VARYING || P->in_width[k] == 0) continue;
+            ok = in[k].batch_stride == 1 && ((uintptr_t)in[k].ptr % 16 == 0) &&
+                 (P->in_width[k] == 1 || (in[k].comp_stride * es) % 16 == 0) && tile_bytes % 16 == 0;
+        }
+        for (size_t k = 0; k < P->out_width.size() && ok; ++k) ok = P->out_width[k] == 0 || out[k].batch_stride == 1;
+        if (ok) {
+            const int64_t ntiles = batch / P->stage_tpb, done = ntiles * P->stage_tpb;
+            rc = launch_one(P, L->fstage, L->grid_stage, ntiles * P->stage_tpb, in, out, params, done, 0, s, P->stage_tpb, P->stage_smem);
+            if (rc) return rc;
+            if (done < batch) rc = launch_one(P, L->fscalar, L->grid_scalar, batch - done, in, out, params, batch - done, done, s);
+            return rc;
+        }
+    }
     if (vec_ok) {
         int64_t nvec = batch / P->vec, done = nvec * P->vec;
         rc = launch_one(P, L->fvec, L->grid_vec, nvec, in, out, params, done, 0, s);
