@@ -190,6 +190,15 @@ class Trace:
     def nan_to_num(self, a, nan):
         return self._emit(rt.OP_NAN_TO_NUM, a, self.const(nan))
 
+    def select_gt0(self, cond, a, b):
+        """cond > 0 ? a : b"""
+        if a == b:
+            return a
+        c = self.const_value(cond)
+        if c is not None:
+            return a if c > 0 else b
+        return self._emit(rt.OP_SELECT_GT0, cond, a, b)
+
     def power(self, a, p):
         if p == 0.5:
             return self.sqrt(a)
@@ -474,6 +483,45 @@ def lower_dense(trace: Trace, kernel, kshape, mask, inputs):
             acc = zero
         out.append(acc)
     return out
+
+
+def lower_inverse(trace: Trace, kernel, n, mask=None):
+    """Inverse of an n x n matrix given as the flattened (row-major) list of value ids: Gauss-Jordan elimination on
+    [A | I] with PARTIAL PIVOTING, fully unrolled into the straight-line IR (row swaps are component-wise selects on
+    |a_ik| - |a_kk| > 0), so a batch of small matrices is inverted by one generated kernel, one matrix per thread,
+    everything in registers.  The counterpart of `np.linalg.inv` on operator kernels (numga/operator/operator.py:78-90,
+    backend/numpy/operator.py `inverse`); same pivoting rule as LAPACK's getrf, results agree to rounding.
+    Entries whose `mask` is False are structural zeros.  Returns the flattened inverse (row-major)."""
+    zero, one = trace.const(0.0), trace.const(1.0)
+    a = [[kernel[i * n + j] if mask is None or mask[i][j] else zero for j in range(n)] for i in range(n)]
+    b = [[one if i == j else zero for j in range(n)] for i in range(n)]
+    for k in range(n):
+        for i in range(k + 1, n):                       # bubble the largest pivot candidate into row k
+            cond = trace.sub(trace.abs(a[i][k]), trace.abs(a[k][k]))
+            if trace.const_value(cond) is not None and not trace.const_value(cond) > 0:
+                continue
+            for rows in (a, b):
+                lo = k if rows is a else 0
+                for j in range(lo, n):
+                    rk, ri = rows[k][j], rows[i][j]
+                    rows[k][j] = trace.select_gt0(cond, ri, rk)
+                    rows[i][j] = trace.select_gt0(cond, rk, ri)
+        p = trace.rcp(a[k][k])
+        for j in range(k + 1, n):
+            a[k][j] = trace.mul(a[k][j], p)
+        for j in range(n):
+            b[k][j] = trace.mul(b[k][j], p)
+        for i in range(n):
+            if i == k:
+                continue
+            f = a[i][k]
+            if trace.is_const(f, 0.0):
+                continue
+            for j in range(k + 1, n):
+                a[i][j] = trace.sub(a[i][j], trace.mul(f, a[k][j]))
+            for j in range(n):
+                b[i][j] = trace.sub(b[i][j], trace.mul(f, b[k][j]))
+    return [b[i][j] for i in range(n) for j in range(n)]
 
 
 # ---- reverse-mode differentiation of a program -----------------------------------------------------------------
