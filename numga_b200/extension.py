@@ -133,6 +133,20 @@ def reverse_scalar_normalized(x):
     return x.symmetric_reverse_product().inverse_square_root() * x
 
 
+@normalized.register(lambda s: s.symmetric_reverse().is_study and s.symmetric_reverse().restrict.nonscalar().is_degenerate)
+def reverse_degenerate_study_normalized(x):
+    """x ~x = s0 + ns with ns nilpotent (3D PGA motors: ns = the pseudoscalar part).  FAST mode uses the closed form
+    (s0 + ns)^(-1/2) = s0^(-1/2) - ns s0^(-3/2) / 2  (one rsqrt instead of sqrt + two reciprocals; the same closed
+    form as the reference's optional `extension/optimized.py:24-50`); FAITHFUL mode runs the reference's default
+    chain square_root().inverse() (norms.py:66-72) operation by operation."""
+    if x.context.faithful:
+        return reverse_study_normalized(x)
+    s = x.symmetric_reverse_product()
+    s0, ns = s.restrict.scalar(), s.restrict.nonscalar()
+    r = s0.inverse_square_root()
+    return (r - ((ns * r) * r) * (r * 0.5)) * x          # ns r^3 / 2, multiplied in an order that cannot under/overflow early
+
+
 @normalized.register(lambda s: s.symmetric_reverse().is_study)
 def reverse_study_normalized(x):
     """4d/5d even grade, e.g. 3D PGA motors: x ~x = (s0, s4) is a Study number (norms.py:66-72).
