@@ -52,6 +52,9 @@ extern "C" {
 #define NGB200_VARYING 0   /* one multivector per batch item            */
 #define NGB200_BROADCAST 1 /* one multivector shared by the whole batch */
 #define NGB200_INDEXED 2   /* item i reads / writes row index[i] (gather / scatter) */
+#define NGB200_REDUCED 3   /* outputs only: ONE multivector = the sum of the per-item results over the batch
+                              (warp shuffle + shared + one atomicAdd per CTA and component); the caller zeroes it.
+                              Used for the gradient of a broadcast operand. */
 
 /* ---- straight-line program IR --------------------------------------------------------------
  * A program maps, independently for every batch item, the components of its input multivectors
@@ -98,7 +101,7 @@ typedef struct ngb200_program_desc {
     const int32_t *input_mode;  /* NGB200_VARYING | BROADCAST | INDEXED */
     int32_t n_outputs;
     const int32_t *output_width;
-    const int32_t *output_mode; /* NGB200_VARYING | INDEXED */
+    const int32_t *output_mode; /* NGB200_VARYING | INDEXED | REDUCED */
     int32_t n_params;           /* runtime scalars (passed as double, cast to dtype) */
     int32_t n_consts;
     const double *consts;

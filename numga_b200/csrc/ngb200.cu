@@ -177,6 +177,7 @@ struct ngb200_program {
     Loaded loaded[kMaxDevices];
     size_t param_bytes = 0;
     bool any_indexed = false;
+    bool any_reduced = false;
     std::mutex host_mu;
     struct HostPipe *host = nullptr;   // staging resources of ngb200_program_run_host, created on first use
 };
@@ -607,8 +608,16 @@ struct Gen {
         }
 
         // ---- scalar kernel: any strides, gather/scatter -----------------------------------
+        int NR = 0;                                   // components summed over the batch (NGB200_REDUCED outputs)
+        std::vector<int> roff(nout, 0);
+        for (int k = 0; k < nout; ++k) if (P.out_mode[k] == NGB200_REDUCED) { roff[k] = NR; NR += P.out_width[k]; }
         appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_scalar(const Params p) {\n");
         appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+        if (NR > 0) {
+            appendf(s, "  __shared__ T ngb_red[%d];\n  T racc[%d];\n", NR, NR);
+            appendf(s, "  for (int j = threadIdx.x; j < %d; j += NGB_TPB) ngb_red[j] = T(0);\n", NR);
+            appendf(s, "  #pragma unroll\n  for (int j = 0; j < %d; ++j) racc[j] = T(0);\n  __syncthreads();\n", NR);
+        }
         s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
         s += "  for (long long i = (long long)blockIdx.x * NGB_TPB + threadIdx.x; i < p.n; i += stride) {\n";
         appendf(s, "    T x[%d]; T y[%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
@@ -623,6 +632,10 @@ struct Gen {
         }
         s += "    ngb_body(x, u, y);\n";
         for (int k = 0; k < nout; ++k) {
+            if (P.out_mode[k] == NGB200_REDUCED) {
+                for (int c = 0; c < P.out_width[k]; ++c) appendf(s, "    racc[%d] += y[%d];\n", roff[k] + c, yoff[k] + c);
+                continue;
+            }
             if (P.out_mode[k] == NGB200_INDEXED)
                 appendf(s, "    T* out%d = p.out[%d].ptr + p.out[%d].index[i] * p.out[%d].bs;\n", k, k, k, k);
             else
@@ -630,7 +643,19 @@ struct Gen {
             for (int c = 0; c < P.out_width[k]; ++c)
                 appendf(s, "    NGB_ST(out%d + %dLL * p.out[%d].cs, y[%d]);\n", k, c, k, yoff[k] + c);
         }
-        s += "  }\n}\n";
+        s += "  }\n";
+        if (NR > 0) {
+            // batch sum: registers -> warp shuffle -> shared atomics -> ONE global atomicAdd per CTA and component
+            appendf(s, "  #pragma unroll\n  for (int j = 0; j < %d; ++j) {\n    T v = racc[j];\n", NR);
+            s += "    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);\n";
+            s += "    if ((threadIdx.x & 31) == 0) atomicAdd(&ngb_red[j], v);\n  }\n  __syncthreads();\n";
+            for (int k = 0; k < nout; ++k) {
+                if (P.out_mode[k] != NGB200_REDUCED) continue;
+                appendf(s, "  for (int c = threadIdx.x; c < %d; c += NGB_TPB) atomicAdd(p.out[%d].ptr + (long long)c * p.out[%d].cs, ngb_red[%d + c]);\n",
+                        P.out_width[k], k, k, roff[k]);
+            }
+        }
+        s += "}\n";
 
         // ---- vector kernel: batch_stride 1, 128-bit accesses --------------------------------
         if (vec > 1 && pair) {
@@ -857,6 +882,7 @@ static int env_int(const char *name, int dflt) {
 static int finish_program(ngb200_program *P, int vec_hint) {
     for (int m : P->in_mode) P->any_indexed |= (m == NGB200_INDEXED);
     for (int m : P->out_mode) P->any_indexed |= (m == NGB200_INDEXED);
+    for (int m : P->out_mode) P->any_reduced |= (m == NGB200_REDUCED);
     Gen gen(*P);
     int rc = gen.analyse();
     if (rc) return rc;
@@ -874,7 +900,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     if (env_int("NGB200_FORCE_VEC", 0) > 0) vec = env_int("NGB200_FORCE_VEC", 0);
     if (vec > vmax) vec = vmax;
     if (vec == 3) vec = 2;
-    if (P->any_indexed || gen.NX == 0) vec = 1;
+    if (P->any_indexed || P->any_reduced || gen.NX == 0) vec = 1;
     // Packed f32x2 arithmetic: measured on B200 (scripts/micro/fp32_rate.cu) scalar FFMA already issues at the full
     // 128 lanes/clk/SM (34.4 T FMA/s) and FFMA2 reaches the same 70 TFLOP/s, so packing buys no throughput and costs
     // registers in large programs; it is kept for the small HBM-bound programs (half the issue slots per item).
@@ -888,7 +914,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     // 2 items/thread: 168 registers -> 3 CTAs of 128 instead of 1 CTA of 256, 4.33 vs 5.86 ms).
     // staged kernel: experimental knob NGB200_STAGE=1 (wide, non-gathered programs only)
     P->stage_tpb = 0;
-    if (env_int("NGB200_STAGE", 0) && !P->any_indexed && gen.NX > 0) {
+    if (env_int("NGB200_STAGE", 0) && !P->any_indexed && !P->any_reduced && gen.NX > 0) {
         P->stage_tpb = env_int("NGB200_STAGE_TPB", 128);
         P->stage_stages = env_int("NGB200_STAGES", 2);
     }
@@ -994,7 +1020,7 @@ extern "C" int ngb200_program_create(const ngb200_program_desc *d, ngb200_progra
     for (int w : P->in_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad input width"); }
     for (int w : P->out_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad output width"); }
     for (int m : P->in_mode) if (m < 0 || m > 2) { delete P; return fail(NGB200_ERR_INVALID, "bad input mode"); }
-    for (int m : P->out_mode) if (m != NGB200_VARYING && m != NGB200_INDEXED) { delete P; return fail(NGB200_ERR_INVALID, "bad output mode"); }
+    for (int m : P->out_mode) if (m != NGB200_VARYING && m != NGB200_INDEXED && m != NGB200_REDUCED) { delete P; return fail(NGB200_ERR_INVALID, "bad output mode"); }
     int rc = finish_program(P, d->vec);
     if (rc) { delete P; return rc; }
     *out = P;

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libnumga_b200.so')
 
 F32, F64 = 0, 1
 FAST, FAITHFUL = 0, 1
-VARYING, BROADCAST, INDEXED = 0, 1, 2
+VARYING, BROADCAST, INDEXED, REDUCED = 0, 1, 2, 3
 
 (OP_INPUT, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SQRT, OP_RSQRT, OP_RCP, OP_ABS,
  OP_NAN_TO_NUM, OP_FMA, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_SELECT_GT0) = range(21)

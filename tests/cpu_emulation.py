@@ -39,6 +39,9 @@ def emulate_launches():
             else:
                 inputs[k] = np.broadcast_to(v, tuple(bshape) + (v.shape[-1],)).reshape(n_batch, v.shape[-1])
         outs = run_ir(self.ir, inputs, np_dtype, params) if n_batch else [np.zeros((0, w), np_dtype) for w in self.ir['out_width']]
+        for k, mode in enumerate(self.program.out_mode):      # NGB200_REDUCED outputs: the batch sum
+            if mode == rt.REDUCED:
+                outs[k] = outs[k][:max(n_batch, 0)].sum(axis=0, keepdims=True)
         result = []
         if out is not None:                                    # in-place destinations (scatter for Indexed)
             for dest, o in zip(out, outs):
@@ -49,7 +52,10 @@ def emulate_launches():
                     dest.values.copy_(torch.as_tensor(np.ascontiguousarray(o)).reshape(dest.values.shape))
                     result.append(dest)
             return result[0] if self.single else tuple(result)
-        for s, o in zip(self.out_subspaces, outs):
+        for k, (s, o) in enumerate(zip(self.out_subspaces, outs)):
+            if self.program.out_mode[k] == rt.REDUCED:
+                result.append(ctx.mvtype(ctx, s, torch.as_tensor(np.ascontiguousarray(o[0])).to(ctx.dtype)))
+                continue
             t = B.to_soa(torch.as_tensor(np.ascontiguousarray(o[:max(n_batch, 1)])).reshape(tuple(bshape) + (len(s),))) \
                 if n_batch > 1 else torch.as_tensor(np.ascontiguousarray(o[:n_batch].reshape(tuple(bshape) + (len(s),))))
             result.append(ctx.mvtype(ctx, s, t.to(ctx.dtype)))

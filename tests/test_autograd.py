@@ -105,3 +105,29 @@ def test_vjp_program_of_a_bilinear_operator_is_the_transposed_table():
     assert vjp['in_width'] == [8, 8, 8] and vjp['out_width'] == [8, 8]
     muls = sum(1 for op, *_ in vjp['instr'] if op == rt.OP_MUL)
     assert muls <= 2 * 64 + 16        # two transposed 64-term tables (+ sharing slack), forward products are dead code
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_broadcast_operand_gradient_is_reduced_inside_the_kernel(where):
+    """d loss / d R for ONE motor applied to a large batch: the backward kernel sums the per-item contributions itself
+    (NGB200_REDUCED output: shuffle + shared + one atomicAdd per CTA) instead of writing batch x 8 values."""
+    from numga_b200 import runtime as rt
+    rng = np.random.default_rng(9)
+    n = (1 << 18) + 77 if where == 'gpu' else 300
+    with _context((3, 0, 1), where) as ctx:
+        S = ctx.subspace
+        R = torch.tensor(rng.standard_normal(8), dtype=torch.float64, device=ctx.device, requires_grad=True)
+        p = ctx.multivector.antivector(rng.standard_normal((n, 4)))
+        w = torch.tensor(rng.standard_normal((n, 4)), dtype=torch.float64, device=ctx.device)
+        f = ctx.jit(lambda r, x: r >> x)
+        loss = (f(ctx.multivector(values=R, subspace=S.even_grade()), p).values * w).sum()
+        loss.backward()
+        compiled = [v for k, v in ctx.engine.cache.items() if k[0][0] == 'jit'][0]
+        assert compiled.vjp().program.out_mode == (rt.REDUCED, rt.VARYING)
+        # reference: the same gradient through per-item motors (no broadcasting, no reduction in the kernel)
+        Rn = R.detach().expand(n, 8).clone().requires_grad_(True)
+        loss2 = (f(ctx.multivector(values=Rn, subspace=S.even_grade()), p).values * w).sum()
+        loss2.backward()
+        want = Rn.grad.sum(dim=0)
+        assert tuple(R.grad.shape) == (8,)
+        assert float((R.grad - want).abs().max() / want.abs().max()) < 1e-10
