@@ -303,7 +303,33 @@ def other_configs(torch, B200Context, rank, peak):
     del x, y, xa, ya
     for dtype, tag in ((torch.float32, 'fp32'), (torch.float64, 'fp64')):
         out.append(physics_config(torch, B200Context, rank, peak, dtype, tag))
+    out.append(training_step_config(torch, B200Context, rank, peak))
     return out
+
+
+def training_step_config(torch, B200Context, rank, peak, n=1 << 26):
+    """Supplementary: forward + backward of the headline operator inside torch.autograd (fit ONE motor to n point
+    correspondences).  The backward pass is the generated VJP kernel; the motor's gradient is reduced in-kernel."""
+    ctx = B200Context((3, 0, 1), dtype=torch.float32)
+    S = ctx.subspace
+    p = device_mv(ctx, S.antivector(), n, 17, rank)
+    q = ctx.multivector.bivector(np.array([0.3, -0.2, 0.1, 0.5, 0.2, -0.4], np.float32)).exp() >> p
+    b = torch.zeros(6, device='cuda', requires_grad=True)
+
+    def sq_err(r, x, y):
+        d = ((r >> x) - y).values
+        return ctx.multivector.scalar(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2] + d[..., 3] * d[..., 3])
+    err = ctx.jit(sq_err)
+
+    def step():
+        b.grad = None
+        loss = err(ctx.multivector(values=b, subspace=S.bivector()).exp(), p, q).values.sum()
+        loss.backward()
+    ms = time_steps(step, 10, 3)
+    nbytes = (16 + 16 + 4 + 4 + 16 + 16 + 4) * n          # fwd: x, y in, err out; torch sum; bwd: x, y, cotangent in
+    return {'config': f'supplementary: autograd training step (fit one motor to 2^{int(np.log2(n))} points: forward + torch sum + generated VJP kernel with in-kernel reduction)',
+            'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': nbytes / n, 'achieved_gbs': nbytes / ms / 1e6,
+            'frac_of_hbm_peak': nbytes / ms / 1e6 / peak, 'grad_finite': bool(torch.isfinite(b.grad).all().item())}
 
 
 def physics_config(torch, B200Context, rank, peak, dtype, tag, n_target=1 << 24):

@@ -525,11 +525,12 @@ def lower_inverse(trace: Trace, kernel, n, mask=None):
 
 
 # ---- reverse-mode differentiation of a program -----------------------------------------------------------------
-def build_vjp(ir, np_dtype, faithful=False):
+def build_vjp(ir, np_dtype, faithful=False, wanted=None):
     """Vector-Jacobian product of a straight-line program as ANOTHER straight-line program (one kernel):
 
         inputs   the original inputs (same addressing modes), then one cotangent operand per original output
-        outputs  one operand per original input: sum_o cotangent[o] * d out[o] / d input   (per batch item)
+        outputs  one operand per original input (or per input listed in `wanted`):
+                 sum_o cotangent[o] * d out[o] / d input   (per batch item)
 
     The forward values are recomputed inside the backward kernel (registers are cheaper than HBM: nothing is saved
     between the passes), then the adjoints are accumulated in reverse program order.  A multilinear operator's
@@ -624,5 +625,6 @@ def build_vjp(ir, np_dtype, faithful=False):
             acc(b, t._emit(rt.OP_SELECT_GT0, a, g, zero)); acc(c, t._emit(rt.OP_SELECT_GT0, a, zero, g))
         else:
             raise NotImplementedError(f'derivative of opcode {op}')
-    outputs = [[adj.get(r, zero) for r in regs] for regs in in_regs]
+    wanted = range(len(in_regs)) if wanted is None else wanted      # only these inputs' cotangents are produced
+    outputs = [[adj.get(r, zero) for r in in_regs[k]] for k in wanted]
     return t.finish(outputs)

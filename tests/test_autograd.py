@@ -123,7 +123,7 @@ def test_broadcast_operand_gradient_is_reduced_inside_the_kernel(where):
         loss = (f(ctx.multivector(values=R, subspace=S.even_grade()), p).values * w).sum()
         loss.backward()
         compiled = [v for k, v in ctx.engine.cache.items() if k[0][0] == 'jit'][0]
-        assert compiled.vjp().program.out_mode == (rt.REDUCED, rt.VARYING)
+        assert compiled.vjp((0,)).program.out_mode == (rt.REDUCED,)      # only R needs a gradient: nothing is written for p
         # reference: the same gradient through per-item motors (no broadcasting, no reduction in the kernel)
         Rn = R.detach().expand(n, 8).clone().requires_grad_(True)
         loss2 = (f(ctx.multivector(values=Rn, subspace=S.even_grade()), p).values * w).sum()
