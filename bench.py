@@ -268,6 +268,20 @@ def other_configs(torch, B200Context, rank, peak):
         entry(f'config 3: exp->normalized->motor_log fused round trip, {tag}, batch 2^{int(np.log2(n))}', ub, n, ms,
               flops=prog.info['n_instr'], note='compute-bound: one kernel, all intermediates in registers; flops = live IR instructions')
         del bv
+    # exp alone: the generic bisection algorithm (the reference's default dispatch) vs the opt-in closed form
+    # (numga_b200.optimized, the counterpart of the reference's optional extension/optimized.py)
+    import numga_b200.optimized as opt
+    c = B200Context((3, 0, 1), dtype=torch.float32)
+    n = 1 << 28
+    bv = device_mv(c, c.subspace.bivector(), n, 13, rank, scale=0.5)
+    for tag, on in (('generic bisection (default dispatch)', False), ('opt-in closed form (numga_b200.optimized)', True)):
+        (opt.enable if on else opt.disable)()
+        f = c.jit(lambda x: x.exp())
+        ms = time_steps(lambda: f(bv), 5, 2)
+        prog = c.engine.cache[next(k for k in c.engine.cache if k[0][0] == 'jit')].program
+        entry(f'config 3 part: bivector exp only, fp32, batch 2^28, {tag}', 56, n, ms, flops=prog.info['n_instr'])
+    opt.disable()
+    del bv
     cga = B200Context((4, 1, 0), dtype=torch.float32)
     F = cga.subspace.full()
     n = 1 << 26

@@ -1,0 +1,91 @@
+"""Opt-in closed forms for 3D PGA (`numga_b200.optimized`), the counterpart of the reference's optional
+`numga/multivector/extension/optimized.py`; tests ported from `extension/test/test_optimized.py:9-52`
+(closed-form normalize / exp == the generic algorithms, atol 1e-8) plus the dispatch bookkeeping."""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from refutil import assert_close, random_non_motor, random_subspace, values_of
+
+
+@contextlib.contextmanager
+def _context(where):
+    if where == 'gpu':
+        from numga_b200 import B200Context
+        yield B200Context('x+y+z+w0', dtype=torch.float64, device='cuda:0')
+    else:
+        from cpu_emulation import emulate_launches, emulated_context
+        with emulate_launches():
+            yield emulated_context('x+y+z+w0', torch.float64, mode='fast')
+
+
+@pytest.fixture
+def optimized():
+    import numga_b200.optimized as opt
+    yield opt
+    opt.disable()
+
+
+WHERE = [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu']
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_normalize(where, optimized):
+    rng = np.random.RandomState(0)
+    with _context(where) as ga:
+        m = random_non_motor(ga, (10,), rng=rng)
+        n1 = m.normalized()
+        optimized.enable()
+        n2 = m.normalized()
+        assert_close(n1, n2)
+        assert_close(n2 * ~n2, 1)
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_exp(where, optimized):
+    rng = np.random.RandomState(0)
+    with _context(where) as ga:
+        B = ga.subspace.bivector()
+        for s in (B, B.degenerate(), B.nondegenerate()):
+            for shape in ((10, 10), ()):
+                b = random_subspace(ga, s, shape, rng)
+                m1 = b.exp_bisect()
+                optimized.enable()
+                m2 = b.exp()
+                optimized.disable()
+                assert m1.subspace.blades.tolist() == m2.subspace.blades.tolist() or len(m2.subspace) <= len(m1.subspace)
+                assert_close(m1, m2.select_subspace(m1.subspace), atol=1e-8)
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_closed_form_exp_is_one_small_kernel_and_handles_pure_translations(where, optimized):
+    with _context(where) as ga:
+        optimized.enable()
+        B = ga.subspace.bivector()
+        f = ga.jit(lambda b: b.exp())
+        z = ga.multivector(B, np.array([[0, 0, 0, 1., 2., 3.], [0, 0, 0, 0, 0, 0], [1e-12, 0, 0, 0.5, 0, 0]]))
+        got = values_of(f(z))
+        assert np.allclose(got[0], [1, 0, 0, 0, 1, 2, 3, 0]) and np.allclose(got[1], [1, 0, 0, 0, 0, 0, 0, 0])
+        assert np.isfinite(got).all()
+        n_closed = len([c for k, c in ga.engine.cache.items() if k[0][0] == 'jit'][0].ir['instr'])
+        optimized.disable()
+        g = ga.jit(lambda b: b.exp())
+        g(z)
+        n_generic = len([c for k, c in ga.engine.cache.items() if k[0][0] == 'jit'][0].ir['instr'])
+        assert n_closed < 60 < 400 < n_generic
+
+
+def test_enable_disable_leave_other_algebras_alone(optimized):
+    from numga_b200 import B200Context
+    optimized.enable()
+    vga = B200Context((3, 0, 0), dtype=torch.float64, device='cpu', compile_only=True)
+    ir, _ = vga.trace(lambda b: b.exp(), vga.subspace.bivector())
+    assert len(ir['instr']) > 100                 # (3,0,0) keeps the generic bisection
+    pga = B200Context((3, 0, 1), dtype=torch.float64, device='cpu', compile_only=True)
+    ir, _ = pga.trace(lambda b: b.exp(), pga.subspace.bivector())
+    assert len(ir['instr']) < 60
+    optimized.disable()
+    ir, _ = pga.trace(lambda b: b.exp(), pga.subspace.bivector())
+    assert len(ir['instr']) > 400
