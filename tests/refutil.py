@@ -52,7 +52,7 @@ def random_non_motor(context, shape=(), scale=1e-2, n=4, rng=None):
 
 
 def values_of(x):
-    v = x.values if hasattr(x, 'values') else x
+    v = x if isinstance(x, (torch.Tensor, np.ndarray)) else (x.values if hasattr(x, 'values') else x)
     return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
 
 

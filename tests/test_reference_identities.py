@@ -216,8 +216,85 @@ def test_inverse_simplification_failure(where):
         assert ga.compile_only or np.allclose(values_of(z.select[5]), 0)
 
 
+def _check_inverse(x, i, atol):
+    assert_close(x * i, 1, atol)
+    assert_close(i * x, 1, atol)
+
+
+@pytest.mark.parametrize('descr,where', _params(INVERSE, [(2, 1, 0)]))
+def test_inverse_compare(descr, where):
+    """backend/test/test_numpy.py:127-153: the dispatched inverse vs the Shirokov (Faddeev-LeVerrier) inverse for
+    vectors, even-grade elements and full multivectors in every signature below 6 dimensions.  (The reference's third
+    method, `inverse_la`, is a numpy-backend helper built on `np.linalg.solve` and is not part of this path.)"""
+    rng = np.random.RandomState(0)
+    with _context(descr, where) as ga:
+        for sub, tol in ((ga.subspace.vector(), 1e-9), (ga.subspace.even_grade(), 1e-8), (ga.subspace.multivector(), 1e-9)):
+            x = random_subspace(ga, sub, (100,), rng)
+            _check_inverse(x, x.inverse(), 1e-12)
+            _check_inverse(x, x.inverse_shirokov(), tol)
+
+
+HITZER = [(1, 0, 0), (0, 1, 0), (2, 0, 0), (1, 1, 0), (0, 2, 0), (3, 0, 0), (2, 1, 0), (1, 2, 0)]
+
+
+@pytest.mark.parametrize('descr,where', _params(HITZER, [(2, 1, 0)]))
+def test_inverse_hitzer(descr, where):
+    """backend/test/test_numpy.py:186-211: non-recursive Hitzer inversion of every grade combination below 4 dimensions."""
+    rng = np.random.RandomState(0)
+    with _context(descr, where) as ga:
+        for grades in _grade_combinations(ga.algebra.n_dimensions + 1):
+            x = random_subspace(ga, ga.subspace.from_grades(grades), (10,), rng)
+            _check_inverse(x, x.inverse_hitzer(), 1e-8)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_geometry_pga3d(where):
+    """backend/test/test_numpy.py:269-276: the motor between two lines maps one onto the other."""
+    rng = np.random.RandomState(0)
+    with _context((3, 0, 1), where) as ga:
+        pairs = random_subspace(ga, ga.subspace.antivector(), (2, 2, 10), rng).normalized()
+        pair1, pair2 = pairs[0], pairs[1]
+        lines = (pair1 & pair2).normalized()
+        l1, l2 = lines[0], lines[1]
+        r = (l1 / l2).motor_square_root()
+        assert_close(l1, r >> l2, atol=1e-9)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_basic_sandwich_equivalences(where):
+    """backend/test/test_numpy.py:11-31: direct product, sandwich operator and the two pre-bound forms agree."""
+    rng = np.random.RandomState(0)
+    with _context('x+y+z+w0', where) as ga:
+        Q, V = ga.subspace.even_grade(), ga.subspace.vector()
+        q, v = random_motor(ga, rng=rng), random_subspace(ga, V, rng=rng)
+        op_partial = ga.operator.sandwich(Q, V).partial({0: q, 2: q})
+        op_partial2 = q.sandwich_map(V)
+        assert np.allclose(values_of(op_partial.kernel), values_of(op_partial2.kernel))
+        r0 = (q * v * ~q).select_subspace(v.subspace)
+        for r in (q.sandwich(v), op_partial(v), op_partial2(v)):
+            assert_close(r0, r)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_translate(where):
+    """backend/test/test_numpy.py:79-107 with its printed quantities turned into assertions (x-y+z+w0)."""
+    with _context('x-y+z+w0', where) as ga:
+        x, y, z, w = ga.multivector.basis()
+        xw, yw = (x ^ w) + 1, (y ^ w) + 1
+        T = xw * yw
+        assert_close(T.symmetric_reverse_product(), 1)             # translators are normalized
+        xy = x ^ y
+        assert_close(xy.symmetric_reverse_product(), -1)           # y is a negative direction: a boost generator
+        v = (x + w).dual()
+        assert_close(T >> (T << v), v)                             # << undoes >>
+        d = x.dual()
+        assert_close(T >> d, d)                                    # directions are left unchanged by translations
+
+
 # (function, parameter list) of every GPU-tier identity test: prewarm compiles their kernels at build time
 GPU_MATRIX = [(test_bisect, LOGEXP), (test_study, STUDY), (test_invariant_decomposition, INVARIANT),
               (test_motor_decompose_euclidean, [(1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1)]), (test_motor_split, SPLIT),
-              (test_study_sqrt, ROOTS), (test_inverse_exhaustive, INVERSE)]
-GPU_SINGLES = [test_object_square_root, test_motor_roots, test_inverse_simplification_failure]
+              (test_study_sqrt, ROOTS), (test_inverse_exhaustive, INVERSE), (test_inverse_compare, INVERSE),
+              (test_inverse_hitzer, HITZER)]
+GPU_SINGLES = [test_object_square_root, test_motor_roots, test_inverse_simplification_failure, test_geometry_pga3d,
+               test_basic_sandwich_equivalences, test_translate]
