@@ -90,13 +90,18 @@ class Trace:
         inner = self._neg_of(a)
         return inner if inner is not None else self._emit(rt.OP_NEG, a)
 
+    def _is_zero(self, vid):
+        """+0.0 or -0.0 (x + (-0.0) == x exactly; x + (+0.0) differs from x only in the sign of a zero)"""
+        c = self.const_value(vid)
+        return c is not None and c == 0
+
     def add(self, a, b):
         f = self._fold(lambda x, y: x + y, a, b)
         if f is not None:
             return f
-        if self.is_const(a, 0.0):
+        if self._is_zero(a):
             return b
-        if self.is_const(b, 0.0):
+        if self._is_zero(b):
             return a
         nb = self._neg_of(b)
         if nb is not None:
@@ -110,9 +115,9 @@ class Trace:
         f = self._fold(lambda x, y: x - y, a, b)
         if f is not None:
             return f
-        if self.is_const(b, 0.0):
+        if self._is_zero(b):
             return a
-        if self.is_const(a, 0.0):
+        if self._is_zero(a):
             return self.neg(b)
         nb = self._neg_of(b)
         if nb is not None:
@@ -130,6 +135,12 @@ class Trace:
                 return self.neg(y)
             if self.is_const(x, 0.0):
                 return x
+        for x, y in ((a, b), (b, a)):
+            cv = self.const_value(x)
+            if cv is not None and cv < 0:
+                # (-c) * y = -(c * y) exactly: 2y and -2y then share one multiply, and the sign folds into the
+                # operand of the consuming add / FMA for free
+                return self.neg(self.mul(self.const(-cv), y))
         na, nb = self._neg_of(a), self._neg_of(b)
         if na is not None and nb is not None:
             return self.mul(na, nb)
@@ -420,7 +431,7 @@ def _row_fast(trace, terms):
             inner = t if inner is None else trace.add(inner, t)
         term = inner if pivot is None else trace.mul(inner, pivot)
         acc = term if acc is None else trace.add(acc, term)
-    return acc
+    return trace.const(0.0) if acc is None else acc        # every term cancelled (e.g. x ^ x on one traced value)
 
 
 def lower_partial(trace: Trace, operator, bound, free, kshape):
