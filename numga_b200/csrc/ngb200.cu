@@ -969,7 +969,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
         rc = nvrtc_compile(P->source, P->cubin);
         if (rc) return rc;
         write_file(base + ".cubin", P->cubin.data(), P->cubin.size());
-        write_file(base + ".cu", P->source.data(), P->source.size());
+        if (env_int("NGB200_CACHE_SOURCES", 0)) write_file(base + ".cu", P->source.data(), P->source.size());
         return NGB200_OK;
     }
     std::string log;
@@ -995,7 +995,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
         }
     }
     write_file(base + ".cubin", P->cubin.data(), P->cubin.size());
-    write_file(base + ".cu", P->source.data(), P->source.size());
+    if (env_int("NGB200_CACHE_SOURCES", 0)) write_file(base + ".cu", P->source.data(), P->source.size());
     return NGB200_OK;
 }
 
