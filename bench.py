@@ -48,22 +48,39 @@ def measured_peaks():
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 50 ms in the background.  `mark()` brackets the timed region; if the region is
-    shorter than the sampling period the same kernel is run on (untimed) until enough samples under load exist,
-    and the summary says so."""
+    """SM clock, power and throttle reasons polled through NVML from a background thread every ~2 ms, so that even a
+    25 ms timed region gets samples DURING it (nvidia-smi's own loop cannot go below ~50 ms; it is the fallback when
+    pynvml is unavailable, in which case the same kernel is kept running, untimed, to observe the clocks under load)."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
         self.t_begin = self.t_end = None
+        self.nvml = None
+        self.stop = False
+        self.source = None
 
     def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.source = 'nvml, ~2 ms period'
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = 'nvidia-smi -lms 50'
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
             t0 = time.time()
@@ -72,6 +89,22 @@ class ClockSampler:
         except Exception:
             self.proc = None
         return self
+
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mw = n.nvmlDeviceGetPowerUsage(self.handle)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                flags = ['Active' if mask & bit else 'Not Active' for _, bit in self.REASONS]
+                self.rows.append((time.time(), [str(sm), str(self.max_sm), str(mw / 1000.0)] + flags))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -84,9 +117,10 @@ class ClockSampler:
         self.t_end = time.time()
 
     def samples_in_region(self):
-        return [r for t, r in self.rows if self.t_begin is not None and t >= self.t_begin and (self.t_end is None or t <= self.t_end + 0.05)]
+        return [r for t, r in self.rows if self.t_begin is not None and t >= self.t_begin and (self.t_end is None or t <= self.t_end + (0.0 if self.nvml else 0.05))]
 
     def __exit__(self, *exc):
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -105,7 +139,7 @@ class ClockSampler:
                 if val.lower().startswith('active'):
                     reasons.add(name)
         out = {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
-               'samples': len(sm), 'power_w_max': max(power) if power else None}
+               'samples': len(sm), 'power_w_max': max(power) if power else None, 'source': self.source}
         if note:
             out['note'] = note
         return out
@@ -422,6 +456,7 @@ def run_ours(args):
         clocks.begin()
         ms = time_steps(lambda: sandwich(R, p), args.steps, 0, dist)
         launches = rt.launch_count() - launches0                    # launches inside the timed region
+        clocks.end()
         note = None
         if len(clocks.samples_in_region()) < 4:
             # the timed region (steps x ~1.3 ms) is shorter than nvidia-smi's sampling period: keep the identical
@@ -431,8 +466,8 @@ def run_ours(args):
                 for _ in range(20):
                     sandwich(R, p)
                 torch.cuda.synchronize()
-            note = 'timed region shorter than the 50 ms sampling period; clocks sampled over the timed region plus a 1 s untimed continuation of the same kernel'
-        clocks.end()
+            note = 'timed region shorter than the sampling period; clocks sampled over the timed region plus a 1 s untimed continuation of the same kernel'
+            clocks.end()
         clock_summary = clocks.summary(note)
     value = world * n / ms * 1e3
     achieved = BYTES_PER_POINT * n / ms / 1e6
