@@ -59,8 +59,35 @@ def main():
             if step in (1, 2, 5):
                 state(f'{pre}/step{step}', b, out)
         assert np.array_equal(out[f'{pre}/step1/motor'], out[f'{pre}/vapply1/motor'])
+    tennis(out)
     np.savez_compressed(os.path.join(HERE, 'physics.npz'), **out)
     print('wrote', len(out), 'arrays')
+
+
+
+def tennis(out):
+    """numga/examples/tennis_racket_theorem.py: free tumbling of point clouds with distinct moments of inertia, one body
+    per spin plane, in 3 and 4 euclidean dimensions (no constraints, no degenerate direction)."""
+    from numga.algebra.algebra import Algebra
+    from numga.examples.physics.core import Body
+    for pqr in ((3, 0, 0), (4, 0, 0)):
+        ctx = NumpyContext(Algebra.from_pqr(*pqr), dtype=np.float64)
+        n = ctx.algebra.description.n_dimensions
+        cube = 2 * ((np.arange(2 ** n)[:, None] & (1 << np.arange(n))) > 0) - 1
+        points = ctx.multivector.vector(cube * (np.arange(n) + 1)).dual()
+        nb = len(ctx.subspace.bivector())
+        body = Body.from_point_cloud(points=points.repeat('... -> b ...', b=nb))
+        jitter = np.random.default_rng(3).standard_normal((nb, nb)) * 1e-5
+        body.rate = body.rate + ctx.multivector.bivector(np.eye(nb) + jitter)
+        tag = 'tennis%d' % n
+        out[f'{tag}/jitter'] = jitter
+        out[f'{tag}/energy0'] = np.array(body.kinetic_energy().values)
+        for step in range(1, 9):
+            body = body.integrate(1 / 4)
+            if step in (1, 8):
+                out[f'{tag}/step{step}/motor'] = np.array(body.motor.values)
+                out[f'{tag}/step{step}/rate'] = np.array(body.rate.values)
+        out[f'{tag}/energy8'] = np.array(body.kinetic_energy().values)
 
 
 if __name__ == '__main__':

@@ -129,3 +129,33 @@ def test_physics_replicated_chains_gpu():
     assert np.array_equal(m, np.broadcast_to(one.motor.values.cpu().numpy(), m.shape))
     assert np.array_equal(r, np.broadcast_to(one.rate.values.cpu().numpy(), r.shape))
     assert np.isfinite(many.kinetic_energy().values.cpu().numpy()).all()
+
+
+# ---- free tumbling (numga/examples/tennis_racket_theorem.py) ------------------------------------------------------------
+def _tennis(ctx, n):
+    from numga_b200.examples.physics import Body
+    cube = 2 * ((np.arange(2 ** n)[:, None] & (1 << np.arange(n))) > 0) - 1
+    points = ctx.multivector.vector(cube * (np.arange(n) + 1)).dual()
+    nb = len(ctx.subspace.bivector())
+    body = Body.from_point_cloud(points=points.repeat('... -> b ...', b=nb))
+    body.rate = body.rate + ctx.multivector.bivector(np.eye(nb) + G[f'tennis{n}/jitter'])
+    assert _err(body.kinetic_energy().values.cpu().numpy(), G[f'tennis{n}/energy0']) < 1e-12
+    for step in range(1, 9):
+        body = body.integrate(1 / 4)
+        if step in (1, 8):
+            assert _err(body.motor.values.cpu().numpy(), G[f'tennis{n}/step{step}/motor']) < 1e-9
+            assert _err(body.rate.values.cpu().numpy(), G[f'tennis{n}/step{step}/rate']) < 1e-9
+    assert _err(body.kinetic_energy().values.cpu().numpy(), G[f'tennis{n}/energy8']) < 1e-9
+
+
+def test_tennis_racket_cpu_emulated():
+    from cpu_emulation import emulate_launches, emulated_context
+    with emulate_launches():
+        _tennis(emulated_context((3, 0, 0), torch.float64), 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [3, 4])
+def test_tennis_racket_gpu(n):
+    from numga_b200 import B200Context
+    _tennis(B200Context((n, 0, 0), dtype=torch.float64, device='cuda:0'), n)
