@@ -98,12 +98,15 @@ def run_job(job):
             for mode in ('fast', 'faithful'):
                 ctx = ctx_of(pqr, dtype, mode)
                 _run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
-    elif kind == 'identity':
+    elif kind in ('identity', 'identity_single'):
         import test_reference_identities as T
-        T.GPU_MATRIX[arg[0]][0](arg[1], 'compile')
-    elif kind == 'identity_single':
-        import test_reference_identities as T
-        T.GPU_SINGLES[arg]('compile')
+        try:
+            if kind == 'identity':
+                T.GPU_MATRIX[arg[0]][0](arg[1], 'compile')
+            else:
+                T.GPU_SINGLES[arg]('compile')
+        except AssertionError:
+            pass        # value assertions mean nothing on uninitialised memory; the kernels up to there are compiled
     return job
 
 

@@ -61,3 +61,19 @@ def assert_close(a, b, atol=1e-9):
     if d.context.compile_only:
         return              # build-time pre-compilation pass: kernels are generated, nothing is computed
     assert np.allclose(values_of(d), 0, atol=atol), float(np.abs(values_of(d)).max())
+
+
+def motor_violations(m, rng=None):
+    """(m ~m - 1, grade-violating part of the full sandwich of a random vector), util.py:70-80."""
+    context = m.context
+    v0 = m.symmetric_reverse_product() - 1
+    V = context.subspace.vector()
+    v = random_subspace(context, V, m.shape, rng)
+    r = context.operator.full_sandwich(m.subspace, v.subspace)(m, v, m)
+    v1 = r.select_subspace(r.subspace.difference(V))
+    return v0, v1
+
+
+def motor_properties(m, rng=None):
+    v0, v1 = motor_violations(m, rng)
+    return np.linalg.norm(values_of(v0), axis=-1), np.linalg.norm(values_of(v1), axis=-1)

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from refutil import assert_close, random_motor, random_non_motor, random_subspace, values_of
+from refutil import assert_close, motor_properties, random_motor, random_non_motor, random_subspace, values_of
 
 
 @contextlib.contextmanager
@@ -293,10 +293,105 @@ def test_translate(where):
         assert_close(T >> d, d)                                    # directions are left unchanged by translations
 
 
+MOTORS = [(2, 0, 0), (1, 0, 1), (1, 1, 0), (3, 0, 0), (2, 0, 1), (2, 1, 0), (1, 1, 1), (4, 0, 0), (3, 0, 1), (3, 1, 0),
+          (2, 1, 1), (5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1), (6, 0, 0), (5, 0, 1), (5, 1, 0), (4, 1, 1), (7, 0, 0),
+          (6, 0, 1), (6, 1, 0), (5, 1, 1)]
+
+
+@pytest.mark.parametrize('descr,where', _params(MOTORS, [(3, 0, 1), (6, 0, 0)]))
+def test_motor_properties(descr, where):
+    """multivector/test/test_normalize.py:12-31: products of bireflections are proper motors (m ~m = 1 and the
+    sandwich of a vector stays a vector) in 2 to 7 dimensions."""
+    rng = np.random.RandomState(0)
+    with _context(descr, where) as ga:
+        m = random_motor(ga, (100,), rng)
+        v0, v1 = motor_properties(m, rng)
+        assert np.allclose(v0, 0, atol=1e-9) and np.allclose(v1, 0, atol=1e-9), (v0.max(), v1.max())
+
+
+@pytest.mark.parametrize('descr,where', _params(MOTORS[:15], [(3, 0, 1), (4, 1, 0)]))
+def test_motor_normalize(descr, where):
+    """multivector/test/test_normalize.py:34-49: analytic normalization through Study numbers, dimensions < 6."""
+    rng = np.random.RandomState(1)
+    with _context(descr, where) as ga:
+        m = random_non_motor(ga, (10,), n=5, rng=rng).normalized()
+        v0, v1 = motor_properties(m, rng)
+        assert np.allclose(v0, 0, atol=1e-9) and np.allclose(v1, 0, atol=1e-9), (v0.max(), v1.max())
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_object_normalize(where):
+    """multivector/test/test_normalize.py:52-71: euclidean points normalize, ideal points do not (their duals do)."""
+    rng = np.random.RandomState(2)
+    with _context((3, 0, 1), where) as ga:
+        P = ga.subspace.antivector()
+        v = random_subspace(ga, P, (10,), rng).normalized()
+        assert_close(v.symmetric_reverse_product(), 1)
+        ideal = random_subspace(ga, P.degenerate(), (10,), rng)
+        with pytest.raises(Exception):
+            ideal.normalized()
+        back = ideal.dual().normalized().dual_inverse()
+        assert back.subspace is ideal.subspace
+        assert_close(back.dual().symmetric_reverse_product(), 1)
+
+
+@pytest.mark.parametrize('descr,where', _params([(2, 0, 0), (1, 0, 1), (3, 0, 0), (2, 0, 1), (4, 0, 0), (3, 0, 1)], [(2, 0, 1)]))
+def test_multivector_normalize(descr, where):
+    """multivector/test/test_normalize.py:74-96: normalization of arbitrary non-null multivectors, dimensions < 5."""
+    rng = np.random.RandomState(3)
+    with _context(descr, where) as ga:
+        for grades in _grade_combinations(ga.algebra.n_dimensions + 1):
+            s = ga.subspace.from_grades(grades)
+            if not s.symmetric_reverse().equals.empty():
+                y = random_subspace(ga, s, (1,), rng).normalized()
+                assert_close(y.symmetric_reverse_product(), 1, atol=1e-6)
+
+
+@pytest.mark.parametrize('descr,where', _params([(5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1), (3, 2, 0)], [(4, 0, 1)]))
+def test_5d_rotor_quality(descr, where):
+    """multivector/test/test_multivector.py:25-36: R ~R = 1 suffices for grade preservation in 5 dimensions."""
+    rng = np.random.RandomState(4)
+    with _context(descr, where) as ga:
+        v = random_subspace(ga, ga.subspace.vector(), (100,), rng)
+        r = random_non_motor(ga, (100,), rng=rng).normalized()
+        assert_close(r.full_sandwich(v).select[5], 0)
+
+
+@pytest.mark.parametrize('where', [pytest.param('gpu', marks=pytest.mark.gpu), 'cpu'])
+def test_multivector_arithmetic_and_at_set(where):
+    """multivector/test/test_multivector.py:10-22 and backend/torch/test/test_torch_benchmark.py:7-27, with their printed
+    quantities turned into assertions: unary +/-, mixed scalar arithmetic, 1 / v, `.at[i].set(...)` on multivectors
+    and on bound operators."""
+    rng = np.random.RandomState(5)
+    with _context('x+y+w0', where) as ga:
+        V = ga.subspace.from_bit_str('100,010,001')
+        assert V is ga.subspace.vector()
+        x = rng.normal(size=3)
+        v = ga.multivector.vector(values=x)
+        assert np.allclose(values_of(+v), x) and np.allclose(values_of(-v), -x)
+        assert np.allclose(values_of(v - 1), np.r_[-1, x]) and np.allclose(values_of(1 - v), np.r_[1, -x])
+        assert np.allclose(values_of(v / 1), x)
+        assert_close((1 / v) * v, 1)
+    with _context('x+y+z+', where) as ga:
+        Q, V = ga.subspace.even_grade(), ga.subspace.vector()
+        q, v = ga.multivector(Q), ga.multivector(subspace=V, values=np.ones(3))
+        assert np.allclose(values_of(q), [1, 0, 0, 0])                   # default values: the unit scalar
+        v2 = v.at[0].set(10)
+        assert np.allclose(values_of(v2), [10, 1, 1]) and np.allclose(values_of(v), [1, 1, 1])      # a copy
+        assert np.allclose(values_of(q.sandwich(v2)), [10, 1, 1])
+        op = q.sandwich_map()
+        assert np.allclose(values_of(op.kernel), np.eye(3))
+        op2 = op.at[0, :].set(0)
+        assert np.allclose(values_of(op2.kernel), np.diag([0., 1, 1])) and np.allclose(values_of(op.kernel), np.eye(3))
+        assert np.allclose(values_of(op2(v2)), [0, 1, 1])
+
+
 # (function, parameter list) of every GPU-tier identity test: prewarm compiles their kernels at build time
 GPU_MATRIX = [(test_bisect, LOGEXP), (test_study, STUDY), (test_invariant_decomposition, INVARIANT),
               (test_motor_decompose_euclidean, [(1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1)]), (test_motor_split, SPLIT),
               (test_study_sqrt, ROOTS), (test_inverse_exhaustive, INVERSE), (test_inverse_compare, INVERSE),
-              (test_inverse_hitzer, HITZER)]
+              (test_inverse_hitzer, HITZER), (test_motor_properties, MOTORS), (test_motor_normalize, MOTORS[:15]),
+              (test_multivector_normalize, [(2, 0, 0), (1, 0, 1), (3, 0, 0), (2, 0, 1), (4, 0, 0), (3, 0, 1)]),
+              (test_5d_rotor_quality, [(5, 0, 0), (4, 0, 1), (4, 1, 0), (3, 1, 1), (3, 2, 0)])]
 GPU_SINGLES = [test_object_square_root, test_motor_roots, test_inverse_simplification_failure, test_geometry_pga3d,
-               test_basic_sandwich_equivalences, test_translate]
+               test_basic_sandwich_equivalences, test_translate, test_object_normalize, test_multivector_arithmetic_and_at_set]
