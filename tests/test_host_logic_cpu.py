@@ -97,3 +97,17 @@ def test_multivector_data_movement_api():
     assert m.select[1].subspace is ctx.subspace.vector()
     assert (m + 1).subspace is m.subspace and (1 + m.select.bivector()).subspace is ctx.subspace.bireflection()
     assert ctx.multivector.ab.subspace.named_str == 'ab'
+
+
+def test_jitted_functions_inline_into_each_other():
+    """A jitted function called from inside another traced function becomes part of the caller's kernel."""
+    ctx = B200Context((3, 0, 1), device='cpu', compile_only=True)
+    S = ctx.subspace
+    inner = ctx.jit(lambda m: m.normalized())
+    outer = ctx.jit(lambda m, p: inner(m) >> p)
+    ir_nested, _ = ctx.trace(lambda m, p: inner(m) >> p, S.even_grade(), S.antivector())
+    ir_flat, _ = ctx.trace(lambda m, p: m.normalized() >> p, S.even_grade(), S.antivector())
+    assert ir_nested['instr'] == ir_flat['instr']
+    n = len(ctx.engine.cache)
+    outer(ctx.multivector.motor(torch.zeros(4, 8)), ctx.multivector.antivector(torch.zeros(4, 4)))
+    assert len(ctx.engine.cache) == n + 1            # one kernel for the whole thing, none for `inner` alone
