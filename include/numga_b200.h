@@ -52,6 +52,9 @@ extern "C" {
 #define NGB200_VARYING 0   /* one multivector per batch item            */
 #define NGB200_BROADCAST 1 /* one multivector shared by the whole batch */
 #define NGB200_INDEXED 2   /* item i reads / writes row index[i] (gather / scatter) */
+#define NGB200_TILED 4     /* inputs only: a PARTIALLY broadcast operand (numpy broadcasting between e.g. [c] and [2, c]
+                              batches): item i reads row (i % inner_size) * batch_stride + (i / inner_size) *
+                              outer_stride, so nothing has to be expanded in memory */
 #define NGB200_REDUCED 3   /* outputs only: ONE multivector = the sum of the per-item results over the batch
                               (warp shuffle + shared + one atomicAdd per CTA and component); the caller zeroes it.
                               Used for the gradient of a broadcast operand. */
@@ -98,7 +101,7 @@ typedef struct ngb200_program_desc {
     uint32_t flags;
     int32_t n_inputs;
     const int32_t *input_width; /* components per input multivector  */
-    const int32_t *input_mode;  /* NGB200_VARYING | BROADCAST | INDEXED */
+    const int32_t *input_mode;  /* NGB200_VARYING | BROADCAST | INDEXED | TILED */
     int32_t n_outputs;
     const int32_t *output_width;
     const int32_t *output_mode; /* NGB200_VARYING | INDEXED | REDUCED */
@@ -117,6 +120,8 @@ typedef struct ngb200_operand {
     int64_t comp_stride;
     int64_t batch_stride;
     const int64_t *index; /* NGB200_INDEXED operands only, else NULL */
+    int64_t inner_size;   /* NGB200_TILED operands only, else 0 */
+    int64_t outer_stride; /* NGB200_TILED operands only, else 0 */
 } ngb200_operand;
 
 typedef struct ngb200_program ngb200_program;

@@ -537,7 +537,7 @@ struct Gen {
         // minimum when it is a real cap
         if (P.minb > 1 && 65536 / (P.tpb * P.minb) < 255) appendf(s, "#define NGB_BOUNDS __launch_bounds__(NGB_TPB, %d)\n", P.minb);
         else s += "#define NGB_BOUNDS __launch_bounds__(NGB_TPB)\n";
-        s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
+        s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; long long inner; long long os; };\n";
         appendf(s, "struct Params { Operand in[%d]; Operand out[%d]; double scal[%d]; long long n; };\n",
                 nin > 0 ? nin : 1, nout > 0 ? nout : 1, P.n_params > 0 ? P.n_params : 1);
         if (f64)
@@ -625,6 +625,9 @@ struct Gen {
             if (P.in_mode[k] == NGB200_BROADCAST) continue;
             if (P.in_mode[k] == NGB200_INDEXED)
                 appendf(s, "    const T* in%d = p.in[%d].ptr + p.in[%d].index[i] * p.in[%d].bs;\n", k, k, k, k);
+            else if (P.in_mode[k] == NGB200_TILED)
+                appendf(s, "    const T* in%d = p.in[%d].ptr + (i %% p.in[%d].inner) * p.in[%d].bs + (i / p.in[%d].inner) * p.in[%d].os;\n",
+                        k, k, k, k, k, k);
             else
                 appendf(s, "    const T* in%d = p.in[%d].ptr + i * p.in[%d].bs;\n", k, k, k);
             for (int c = 0; c < P.in_width[k]; ++c)
@@ -880,7 +883,7 @@ static int env_int(const char *name, int dflt) {
 }
 
 static int finish_program(ngb200_program *P, int vec_hint) {
-    for (int m : P->in_mode) P->any_indexed |= (m == NGB200_INDEXED);
+    for (int m : P->in_mode) P->any_indexed |= (m == NGB200_INDEXED || m == NGB200_TILED);    // scalar kernel only
     for (int m : P->out_mode) P->any_indexed |= (m == NGB200_INDEXED);
     for (int m : P->out_mode) P->any_reduced |= (m == NGB200_REDUCED);
     Gen gen(*P);
@@ -939,7 +942,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
         P->stage_nx = gen.NX;
         P->stage_smem = (size_t)P->stage_stages * gen.NX * P->stage_tpb * esize(P->dtype);
     };
-    P->param_bytes = 32 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
+    P->param_bytes = 48 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
     if (P->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel (%zu parameter bytes)", P->param_bytes);
 
@@ -1019,7 +1022,7 @@ extern "C" int ngb200_program_create(const ngb200_program_desc *d, ngb200_progra
     if (d->n_stores) P->stores.assign(d->stores, d->stores + d->n_stores);
     for (int w : P->in_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad input width"); }
     for (int w : P->out_width) if (w < 0 || w > 4096) { delete P; return fail(NGB200_ERR_INVALID, "bad output width"); }
-    for (int m : P->in_mode) if (m < 0 || m > 2) { delete P; return fail(NGB200_ERR_INVALID, "bad input mode"); }
+    for (int m : P->in_mode) if (m != NGB200_VARYING && m != NGB200_BROADCAST && m != NGB200_INDEXED && m != NGB200_TILED) { delete P; return fail(NGB200_ERR_INVALID, "bad input mode"); }
     for (int m : P->out_mode) if (m != NGB200_VARYING && m != NGB200_INDEXED && m != NGB200_REDUCED) { delete P; return fail(NGB200_ERR_INVALID, "bad output mode"); }
     int rc = finish_program(P, d->vec);
     if (rc) { delete P; return rc; }
@@ -1208,6 +1211,7 @@ struct DevOperand {
     void *ptr;
     long long cs, bs;
     const long long *index;
+    long long inner, os;
 };
 
 static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t work, const ngb200_operand *in,
@@ -1223,17 +1227,18 @@ static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t wor
         bool moves = P->in_mode[k] == NGB200_VARYING;
         o[k] = {(char *)in[k].ptr + (moves ? offset * in[k].batch_stride * es : 0), in[k].comp_stride,
                 P->in_mode[k] == NGB200_BROADCAST ? 0 : in[k].batch_stride,
-                P->in_mode[k] == NGB200_INDEXED ? (const long long *)in[k].index + offset : nullptr};
+                P->in_mode[k] == NGB200_INDEXED ? (const long long *)in[k].index + offset : nullptr,
+                P->in_mode[k] == NGB200_TILED ? in[k].inner_size : 0, P->in_mode[k] == NGB200_TILED ? in[k].outer_stride : 0};
     }
     for (size_t k = 0; k < nout; ++k) {
         bool moves = P->out_mode[k] == NGB200_VARYING;
         o[nin_s + k] = {(char *)out[k].ptr + (moves ? offset * out[k].batch_stride * es : 0), out[k].comp_stride,
                         out[k].batch_stride,
-                        P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr};
+                        P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr, 0, 0};
     }
-    double *sc = reinterpret_cast<double *>(buf.data() + 32 * (nin_s + nout_s));
+    double *sc = reinterpret_cast<double *>(buf.data() + 48 * (nin_s + nout_s));
     for (int k = 0; k < P->n_params; ++k) sc[k] = params ? params[k] : 0.0;
-    *reinterpret_cast<long long *>(buf.data() + 32 * (nin_s + nout_s) + 8 * np_s) = n;
+    *reinterpret_cast<long long *>(buf.data() + 48 * (nin_s + nout_s) + 8 * np_s) = n;
     int64_t blocks = (work + tpb - 1) / tpb;
     if (blocks > grid_cap) blocks = grid_cap;
     if (blocks < 1) blocks = 1;
@@ -1261,6 +1266,7 @@ extern "C" int ngb200_program_launch(ngb200_program *P, const ngb200_operand *in
     for (size_t k = 0; k < P->in_width.size(); ++k) {
         if (P->in_width[k] > 0 && !in[k].ptr) return fail(NGB200_ERR_INVALID, "input %zu: null pointer", k);
         if (P->in_mode[k] == NGB200_INDEXED && !in[k].index) return fail(NGB200_ERR_INVALID, "input %zu: indexed operand without index", k);
+        if (P->in_mode[k] == NGB200_TILED && in[k].inner_size <= 0) return fail(NGB200_ERR_INVALID, "input %zu: tiled operand needs inner_size > 0", k);
     }
     for (size_t k = 0; k < P->out_width.size(); ++k) {
         if (P->out_width[k] > 0 && !out[k].ptr) return fail(NGB200_ERR_INVALID, "output %zu: null pointer", k);

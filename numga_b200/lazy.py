@@ -143,15 +143,61 @@ class LazyEngine:
     def apply_method(self, name, static_positions, args):
         return self.apply(name, _method_caller(name), static_positions, args)
 
+    def gather(self, base, idx):
+        """`base[idx]` for an integer index over a one-dimensional batch: nothing is copied; the kernel that consumes
+        the result reads the rows through an index operand (NGB200_INDEXED)."""
+        import torch
+        from numga_b200.backend import Indexed
+        if isinstance(base, self.cls) and base._values is None:
+            if base._node.key == 'gather':
+                base.values                         # gather of a gather: resolve the inner one with torch
+            else:
+                self.realize([base])
+        if not isinstance(idx, torch.Tensor):
+            idx = torch.as_tensor(np.asarray(idx), device=self.context.device)
+        node = _Node('gather', None, (base, idx), (('gather',),), 0)
+        lazy = self.cls(self.context, base.subspace, node, tuple(idx.shape))
+        lazy._indexed = Indexed(base, idx)
+        return lazy
+
+    def scatter(self, rebuild, arr, idx, values):
+        """`x.at[idx].set(values)` with pending `values`: the copy of x is made once and the kernel that computes the
+        values writes them straight into its rows.  Returns None when this form does not apply."""
+        import torch
+        from numga_b200.backend import Indexed, _is_row_index
+        if not (isinstance(values, self.cls) and values._values is None and values._node.key != 'gather'):
+            return None
+        if not (_is_row_index(idx) and isinstance(arr, torch.Tensor) and arr.dim() == 2):
+            return None
+        if not isinstance(idx, torch.Tensor):
+            idx = torch.as_tensor(np.asarray(idx), device=self.context.device)
+        if tuple(values.shape) != tuple(idx.shape):
+            return None
+        dest = rebuild(arr.clone())
+        if not isinstance(dest, MultiVector) or dest.subspace is not values.subspace:
+            return None
+        self.realize([values], out=(Indexed(dest, idx),))
+        return dest
+
     # ---- materialisation ------------------------------------------------------------------------------------------------
-    def realize(self, targets):
+    def realize(self, targets, out=None):
         """Compute all pending `targets` (LazyMultiVectors) with ONE kernel.  Pending intermediates of the DAG that are
         still referenced from outside it (a python variable, another pending expression) are written by the same
         kernel, so nothing is computed twice later; intermediates only the DAG knows stay in registers."""
         targets = [t for t in targets if isinstance(t, self.cls) and t._values is None]
+        for t in [t for t in targets if t._node.key == 'gather']:      # a bare gather asked for its values: torch does it
+            from numga_b200.backend import as_soa
+            base, idx = t._node.args
+            t.values = as_soa(base.values[idx])
+        targets = [t for t in targets if t._values is None]
         if not targets:
             return
+        if len({t.shape for t in targets}) > 1:           # one kernel = one batch shape
+            for t in targets:
+                self.realize([t])
+            return
         ctx = self.context
+        bshape = targets[0].shape
         order, fns, index, leaves, leaf_index = [], [], {}, [], {}
         inner, dag_refs = {}, {}                # pending multivectors met as arguments, and how often the DAG refers to them
 
@@ -168,7 +214,13 @@ class LazyEngine:
             refs = []
             for a, d in zip(node.args, node.static):
                 if d[0] == 'mv':
-                    if isinstance(a, self.cls) and a._values is None:
+                    if isinstance(a, self.cls) and a._values is None and a._node.key == 'gather':
+                        if a.shape != bshape:
+                            a.values          # a gather over a smaller batch than the kernel's: resolved by torch,
+                            refs.append(('l', leaf(a)))                # then broadcast like any other operand
+                        else:
+                            refs.append(('l', leaf(a._indexed)))       # gathered inside the kernel
+                    elif isinstance(a, self.cls) and a._values is None:
                         inner[id(a)] = a
                         dag_refs[id(a)] = dag_refs.get(id(a), 0) + 1
                         refs.append(('n', visit(a)))
@@ -190,7 +242,9 @@ class LazyEngine:
             visit(t)
         target_ids = {id(t) for t in targets}
         # references to an intermediate beyond those of the DAG itself mean somebody will ask for it again
-        extra = [mv for mv, n in _outside_references(inner, dag_refs) if n > 0 and id(mv) not in target_ids]
+        extra = [] if out is not None else \
+            [mv for mv, n in _outside_references(inner, dag_refs)
+             if n > 0 and id(mv) not in target_ids and mv.shape == bshape]
         results = targets + extra
         outs = tuple(index[id(t._node)] for t in results)
         structure = (tuple(order), outs)
@@ -203,6 +257,9 @@ class LazyEngine:
             result = tuple(vals[o] for o in outs)
             return result[0] if len(result) == 1 else result
 
+        if out is not None:                       # results are written / scattered into caller-owned destinations
+            ctx.engine.call(('lazy', structure), replay, tuple(leaves), out=out)
+            return
         computed = ctx.engine.call(('lazy', structure), replay, tuple(leaves))
         computed = (computed,) if len(results) == 1 else computed
         for t, r in zip(results, computed):

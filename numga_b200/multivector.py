@@ -25,6 +25,11 @@ class _IndexSetter:
         return _IndexSetter(self._rebuild, self._arr, self._context, idx)
 
     def set(self, values):
+        lazy = getattr(self._context, 'lazy_engine', None)
+        if lazy is not None and self._context.lazy and isinstance(values, MultiVector):
+            scattered = lazy.scatter(self._rebuild, self._arr, self._idx, values)
+            if scattered is not None:
+                return scattered                      # rows written in place by the kernel that computes them
         if isinstance(values, MultiVector):
             values = values.values
         return self._rebuild(self._context.set_array(self._arr, self._idx, values))

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libnumga_b200.so')
 
 F32, F64 = 0, 1
 FAST, FAITHFUL = 0, 1
-VARYING, BROADCAST, INDEXED, REDUCED = 0, 1, 2, 3
+VARYING, BROADCAST, INDEXED, REDUCED, TILED = 0, 1, 2, 3, 4
 
 (OP_INPUT, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SQRT, OP_RSQRT, OP_RCP, OP_ABS,
  OP_NAN_TO_NUM, OP_FMA, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_SELECT_GT0) = range(21)
@@ -48,7 +48,8 @@ class ProgramDesc(C.Structure):
 
 
 class Operand(C.Structure):
-    _fields_ = [('ptr', C.c_void_p), ('comp_stride', C.c_int64), ('batch_stride', C.c_int64), ('index', C.c_void_p)]
+    _fields_ = [('ptr', C.c_void_p), ('comp_stride', C.c_int64), ('batch_stride', C.c_int64), ('index', C.c_void_p),
+                ('inner_size', C.c_int64), ('outer_stride', C.c_int64)]
 
 
 class ProgramInfo(C.Structure):
@@ -174,11 +175,12 @@ class Program:
     def _operands(specs):
         arr = (Operand * max(len(specs), 1))()
         for k, (ptr, cs, bs, *rest) in enumerate(specs):
-            arr[k] = Operand(ptr, cs, bs, rest[0] if rest else None)
+            arr[k] = Operand(ptr, cs, bs, rest[0] if rest else None, rest[1] if len(rest) > 1 else 0,
+                             rest[2] if len(rest) > 2 else 0)
         return arr
 
     def launch(self, inputs, outputs, batch, stream=0, params=()):
-        """inputs/outputs: sequences of (device_ptr, comp_stride, batch_stride[, index_ptr])."""
+        """inputs/outputs: sequences of (device_ptr, comp_stride, batch_stride[, index_ptr[, inner_size, outer_stride]])."""
         assert len(inputs) == len(self.in_width) and len(outputs) == len(self.out_width)
         p = (C.c_double * max(len(params), 1))(*params)
         check(lib.ngb200_program_launch(self.handle, self._operands(inputs), self._operands(outputs), p,

@@ -30,6 +30,34 @@ if which == 'physics_time':
     r = physics_config(torch, B200Context, 0, measured_peaks()[0], torch.float64 if 'f64' in sys.argv else torch.float32, 'fp')
     print(which, {k: v for k, v in os.environ.items() if k.startswith('NGB200') and 'CACHE' not in k}, f"{r['ms']:.3f} ms {r['items_per_s']/1e9:.3f} G/s {r['achieved_gbs']:.0f} GB/s")
     sys.exit(0)
+if which == 'physics_generic_time':
+    # the reference-style Body.integrate (numga/examples/physics/core.py, unchanged formulas) at benchmark size:
+    # eager (one kernel per multivector method), lazy (automatic fusion), and the hand-arranged FusedStep
+    from bench import time_steps
+    from numga_b200 import runtime as rt
+    from numga_b200.examples.physics import FusedStep, replicate_chains, setup_bodies
+    n_chains = (1 << int(os.environ.get('LOGN', '22'))) // 12
+    for mode in os.environ.get('MODES', 'eager,lazy,fused').split(','):
+        ctx = B200Context('x+y+z+w0', lazy=(mode == 'lazy'))
+        bodies, sets = setup_bodies(ctx, n_bodies=12)
+        big, bsets = replicate_chains(bodies, sets, n_chains)
+        big = big.copy(rate=big.rate + device_mv(ctx, ctx.subspace.bivector(), 12 * n_chains, 16, 0, scale=0.3))
+        big.rate.values
+        state = [big]
+        if mode == 'fused':
+            fs = FusedStep(big, bsets)
+            def step(): state[0] = fs.integrate(state[0], 1 / 200)
+        else:
+            def step():
+                new = state[0].integrate(1 / 200, bsets)
+                new.motor.values; new.rate.values
+                state[0] = new
+        l0 = rt.launch_count(); step(); torch.cuda.synchronize(); launches = rt.launch_count() - l0
+        ms = time_steps(step, 5, 2)
+        print(which, mode, f'{12 * n_chains} bodies: {ms:.3f} ms per sub-step, {launches} generated-kernel launches, {12 * n_chains / ms / 1e6:.3f} G body-steps/s', flush=True)
+        del big, bsets, state
+        torch.cuda.empty_cache()
+    sys.exit(0)
 if which == 'cga_pitch':
     from bench import time_steps
     ctx = B200Context((4, 1, 0)); F = ctx.subspace.full(); n = 1 << 26

@@ -31,7 +31,8 @@ def emulate_launches():
         inputs = [None] * len(mvs)
         for k, a in mvs:
             if isinstance(a, B.Indexed):                       # gather
-                inputs[k] = a.as_mv().values.detach().cpu().numpy()[a.index.cpu().numpy()]
+                g = a.as_mv().values.detach().cpu().numpy()[a.index.cpu().numpy()]
+                inputs[k] = g.reshape(-1, g.shape[-1])
                 continue
             v = a.values.detach().cpu().numpy()
             if self.program.in_mode[k] == rt.BROADCAST:
@@ -46,7 +47,8 @@ def emulate_launches():
         if out is not None:                                    # in-place destinations (scatter for Indexed)
             for dest, o in zip(out, outs):
                 if isinstance(dest, B.Indexed):
-                    dest.as_mv().values[dest.index] = torch.as_tensor(np.ascontiguousarray(o)).to(ctx.dtype)
+                    rows = torch.as_tensor(np.ascontiguousarray(o)).to(ctx.dtype)
+                    dest.as_mv().values[dest.index] = rows.reshape(tuple(dest.index.shape) + (rows.shape[-1],))
                     result.append(dest.target)
                 else:
                     dest.values.copy_(torch.as_tensor(np.ascontiguousarray(o)).reshape(dest.values.shape))

@@ -314,3 +314,21 @@ def test_staged_bulk_copy_kernel_variant_is_bit_identical(monkeypatch):
     prog = list(staged.engine.cache.values())[-1].program
     assert 'ngb_stage' in prog.source and 'cp.async.bulk' in prog.source
     assert np.array_equal(res.numpy(), want)
+
+
+@pytest.mark.parametrize('shapes', [((2, 300), (300,)), ((2, 300), (2, 1)), ((4, 2, 50), (2, 50)), ((4, 2, 50), (4, 1, 1)),
+                                    ((300,), (2, 300)), ((2, 5, 3), (2, 1, 3)), ((3, 1, 7), (1, 4, 1))])
+def test_partially_broadcast_operands_are_addressed_in_the_kernel(shapes):
+    """numpy broadcasting between batches of different rank / extent (NGB200_TILED operands: item i reads row
+    (i % inner) * s + (i // inner) * S); irregular patterns fall back to one expanding copy.  Against the oracle."""
+    from numga_b200 import runtime as rt
+    ctx = _ctx((3, 0, 1), np.float64)
+    octx = O.context((3, 0, 1), np.float64)
+    rng = np.random.default_rng(31)
+    a, b = rng.standard_normal(shapes[0] + (8,)), rng.standard_normal(shapes[1] + (4,))
+    want = (octx.multivector('even_grade', a) >> octx.multivector('antivector', b)).values
+    got = ctx.multivector.motor(a) >> ctx.multivector.antivector(b)
+    assert got.shape == np.broadcast_shapes(*shapes) and _rel_err(got.numpy(), want) < 1e-12
+    modes = list(ctx.engine.cache.values())[-1].program.in_mode
+    regular = shapes not in [((2, 5, 3), (2, 1, 3)), ((3, 1, 7), (1, 4, 1))]
+    assert (rt.TILED in modes) == regular

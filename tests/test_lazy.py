@@ -125,3 +125,23 @@ def test_pending_dag_is_bounded(where):
         for _ in range(40):
             ref = ref * rr
         assert np.allclose(_np(m), _np(ref), atol=1e-12)
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_lazy_gathers_of_different_batch_shapes(where):
+    """Replicated chains: per-constraint data gathered lazily over [c] items meets kernels over [2, c] items; a gather
+    is done inside a kernel only when its index covers that kernel's whole batch, otherwise torch resolves it."""
+    from numga_b200.examples.physics import replicate_chains, setup_bodies
+    rng = np.random.default_rng(0)
+    jitter = 0.3 * rng.standard_normal((600, 6))
+    with _contexts('x+y+z+w0', where) as (eager, lazy, counter):
+        states = {}
+        for name, ctx in (('eager', eager), ('lazy', lazy)):
+            bodies, sets = setup_bodies(ctx, n_bodies=12)
+            big, bsets = replicate_chains(bodies, sets, 50)
+            b = big.copy(rate=big.rate + ctx.multivector.bivector(jitter))
+            for _ in range(2):
+                b = b.integrate(1 / 200, bsets)
+            states[name] = (_np(b.motor), _np(b.rate))
+        assert np.abs(states['lazy'][0] - states['eager'][0]).max() < 1e-13
+        assert np.abs(states['lazy'][1] - states['eager'][1]).max() < 1e-10
