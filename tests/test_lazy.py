@@ -145,3 +145,25 @@ def test_lazy_gathers_of_different_batch_shapes(where):
             states[name] = (_np(b.motor), _np(b.rate))
         assert np.abs(states['lazy'][0] - states['eager'][0]).max() < 1e-13
         assert np.abs(states['lazy'][1] - states['eager'][1]).max() < 1e-10
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_autograd_through_a_lazily_fused_chain(where):
+    """A recorded chain with a `requires_grad` leaf: one fused forward kernel, one generated backward kernel, same
+    gradient as the eager path."""
+    rng = np.random.default_rng(0)
+    b0, pv, qv = 0.3 * rng.standard_normal(6), rng.standard_normal((9, 4)), rng.standard_normal((9, 4))
+    with _contexts((3, 0, 1), where) as (eager, lazy, counter):
+        grads = {}
+        for name, ctx in (('eager', eager), ('lazy', lazy)):
+            b = torch.tensor(b0, dtype=torch.float64, device=ctx.device, requires_grad=True)
+            p = ctx.multivector.antivector(pv)
+            q = torch.tensor(qv, dtype=torch.float64, device=ctx.device)
+            out = (ctx.multivector(values=b, subspace=ctx.subspace.bivector()).exp() >> p) + p * 0.5
+            counter['n'] = 0
+            loss = ((out.values - q) ** 2).sum()
+            launches_fwd = counter['n']
+            loss.backward()
+            grads[name] = (b.grad.detach().cpu().numpy(), launches_fwd, counter['n'] - launches_fwd)
+        assert np.allclose(grads['lazy'][0], grads['eager'][0], atol=1e-12)
+        assert grads['lazy'][1] == 1 and grads['lazy'][2] == 1           # one forward kernel, one backward kernel
