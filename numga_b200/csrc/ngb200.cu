@@ -178,6 +178,7 @@ struct ngb200_program {
     size_t param_bytes = 0;
     bool any_indexed = false;
     bool any_reduced = false;
+    bool any_tiled = false;       // some input is NGB200_TILED: operands carry (inner, outer stride) -> 48-byte layout
     std::mutex host_mu;
     struct HostPipe *host = nullptr;   // staging resources of ngb200_program_run_host, created on first use
 };
@@ -537,7 +538,10 @@ struct Gen {
         // minimum when it is a real cap
         if (P.minb > 1 && 65536 / (P.tpb * P.minb) < 255) appendf(s, "#define NGB_BOUNDS __launch_bounds__(NGB_TPB, %d)\n", P.minb);
         else s += "#define NGB_BOUNDS __launch_bounds__(NGB_TPB)\n";
-        s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; long long inner; long long os; };\n";
+        // (the two extra fields only exist in programs with a TILED operand: the plain 32-byte layout is kept elsewhere
+        //  because the widest kernels are sensitive to ptxas' scheduling: CGA full x full lost 10 % with the larger one)
+        if (P.any_tiled) s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; long long inner; long long os; };\n";
+        else s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
         appendf(s, "struct Params { Operand in[%d]; Operand out[%d]; double scal[%d]; long long n; };\n",
                 nin > 0 ? nin : 1, nout > 0 ? nout : 1, P.n_params > 0 ? P.n_params : 1);
         if (f64)
@@ -886,6 +890,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     for (int m : P->in_mode) P->any_indexed |= (m == NGB200_INDEXED || m == NGB200_TILED);    // scalar kernel only
     for (int m : P->out_mode) P->any_indexed |= (m == NGB200_INDEXED);
     for (int m : P->out_mode) P->any_reduced |= (m == NGB200_REDUCED);
+    for (int m : P->in_mode) P->any_tiled |= (m == NGB200_TILED);
     Gen gen(*P);
     int rc = gen.analyse();
     if (rc) return rc;
@@ -942,7 +947,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
         P->stage_nx = gen.NX;
         P->stage_smem = (size_t)P->stage_stages * gen.NX * P->stage_tpb * esize(P->dtype);
     };
-    P->param_bytes = 48 * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
+    P->param_bytes = (P->any_tiled ? 48 : 32) * ((P->in_width.size() ? P->in_width.size() : 1) + (P->out_width.size() ? P->out_width.size() : 1)) +
                      8 * (P->n_params > 0 ? P->n_params : 1) + 8;
     if (P->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel (%zu parameter bytes)", P->param_bytes);
 
@@ -1221,24 +1226,25 @@ static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t wor
     const size_t nin = P->in_width.size(), nout = P->out_width.size();
     const size_t nin_s = nin ? nin : 1, nout_s = nout ? nout : 1, np_s = P->n_params > 0 ? P->n_params : 1;
     std::vector<char> buf(P->param_bytes, 0);
-    DevOperand *o = reinterpret_cast<DevOperand *>(buf.data());
+    const size_t ob = P->any_tiled ? 48 : 32;          // bytes per operand in the kernel's Params
     const int es = esize(P->dtype);
+    auto put = [&](size_t slot, const DevOperand &d) { memcpy(buf.data() + slot * ob, &d, ob); };
     for (size_t k = 0; k < nin; ++k) {
         bool moves = P->in_mode[k] == NGB200_VARYING;
-        o[k] = {(char *)in[k].ptr + (moves ? offset * in[k].batch_stride * es : 0), in[k].comp_stride,
+        put(k, {(char *)in[k].ptr + (moves ? offset * in[k].batch_stride * es : 0), in[k].comp_stride,
                 P->in_mode[k] == NGB200_BROADCAST ? 0 : in[k].batch_stride,
                 P->in_mode[k] == NGB200_INDEXED ? (const long long *)in[k].index + offset : nullptr,
-                P->in_mode[k] == NGB200_TILED ? in[k].inner_size : 0, P->in_mode[k] == NGB200_TILED ? in[k].outer_stride : 0};
+                P->in_mode[k] == NGB200_TILED ? in[k].inner_size : 0, P->in_mode[k] == NGB200_TILED ? in[k].outer_stride : 0});
     }
     for (size_t k = 0; k < nout; ++k) {
         bool moves = P->out_mode[k] == NGB200_VARYING;
-        o[nin_s + k] = {(char *)out[k].ptr + (moves ? offset * out[k].batch_stride * es : 0), out[k].comp_stride,
+        put(nin_s + k, {(char *)out[k].ptr + (moves ? offset * out[k].batch_stride * es : 0), out[k].comp_stride,
                         out[k].batch_stride,
-                        P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr, 0, 0};
+                        P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr, 0, 0});
     }
-    double *sc = reinterpret_cast<double *>(buf.data() + 48 * (nin_s + nout_s));
+    double *sc = reinterpret_cast<double *>(buf.data() + ob * (nin_s + nout_s));
     for (int k = 0; k < P->n_params; ++k) sc[k] = params ? params[k] : 0.0;
-    *reinterpret_cast<long long *>(buf.data() + 48 * (nin_s + nout_s) + 8 * np_s) = n;
+    *reinterpret_cast<long long *>(buf.data() + ob * (nin_s + nout_s) + 8 * np_s) = n;
     int64_t blocks = (work + tpb - 1) / tpb;
     if (blocks > grid_cap) blocks = grid_cap;
     if (blocks < 1) blocks = 1;
