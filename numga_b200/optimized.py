@@ -122,3 +122,4 @@ def _invalidate():
     for ctx in list(B200Context.instances):
         ctx.engine.cache.clear()
         ctx.engine.fast_cache.clear()
+        ctx.lazy_engine.signatures.clear()
