@@ -103,3 +103,36 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in text.replace('numga_oracle', 'oracle') or f == 'ngb200.cu' and 'oracle' not in text, \
                     f'{f} mentions the oracle: product code must not depend on it'
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The header is plain C (compiles with gcc, no C++ / CUDA types) and the ctypes mirror in runtime.py has the same
+    struct sizes and field offsets."""
+    import ctypes
+    import subprocess
+    src = tmp_path / 'layout.c'
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "numga_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ngb200_operand), offsetof(ngb200_operand, comp_stride),
+           offsetof(ngb200_operand, batch_stride), offsetof(ngb200_operand, index), offsetof(ngb200_operand, inner_size),
+           offsetof(ngb200_operand, outer_stride), sizeof(ngb200_instr));
+    printf("%zu %zu %zu %zu\\n", sizeof(ngb200_program_desc), offsetof(ngb200_program_desc, consts),
+           offsetof(ngb200_program_desc, stores), offsetof(ngb200_program_desc, vec));
+    printf("%zu %zu\\n", sizeof(ngb200_program_info), offsetof(ngb200_program_info, cubin_bytes));
+    printf("%d %d %d %d %d\\n", NGB200_VARYING, NGB200_BROADCAST, NGB200_INDEXED, NGB200_REDUCED, NGB200_TILED);
+    return 0;
+}
+''')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split('\n')
+    op = rt.Operand
+    assert lines[0].split() == [str(x) for x in (ctypes.sizeof(op), op.comp_stride.offset, op.batch_stride.offset, op.index.offset,
+                                                  op.inner_size.offset, op.outer_stride.offset, ctypes.sizeof(rt.Instr))]
+    d = rt.ProgramDesc
+    assert lines[1].split() == [str(x) for x in (ctypes.sizeof(d), d.consts.offset, d.stores.offset, d.vec.offset)]
+    assert lines[2].split() == [str(ctypes.sizeof(rt.ProgramInfo)), str(rt.ProgramInfo.cubin_bytes.offset)]
+    assert lines[3].split() == [str(x) for x in (rt.VARYING, rt.BROADCAST, rt.INDEXED, rt.REDUCED, rt.TILED)]
