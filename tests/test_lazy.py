@@ -105,7 +105,7 @@ def test_reference_style_physics_step_fuses_automatically(where):
             m, r = _np(new.motor), _np(new.rate)
             launches[name] = counter['n']
             assert np.abs(m - G['f64/step1/motor']).max() < 1e-12 and np.abs(r - G['f64/step1/rate']).max() < 1e-10
-        assert launches['lazy'] < 20 < 100 < launches['eager']
+        assert launches["lazy"] <= 8 < 100 < launches["eager"]
 
 
 @pytest.mark.parametrize('where', WHERE)
