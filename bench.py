@@ -352,6 +352,39 @@ def other_configs(torch, B200Context, rank, peak):
     for dtype, tag in ((torch.float32, 'fp32'), (torch.float64, 'fp64')):
         out.append(physics_config(torch, B200Context, rank, peak, dtype, tag))
     out.append(training_step_config(torch, B200Context, rank, peak))
+    out.extend(generic_physics_configs(torch, B200Context, rank, peak))
+    return out
+
+
+def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22):
+    """Supplementary: the rigid-body step written exactly like the reference (Body.integrate, one multivector method
+    after the other), run eagerly (one kernel per method) and with automatic fusion (B200Context(lazy=True))."""
+    from numga_b200 import runtime as rt
+    from numga_b200.examples.physics import replicate_chains, setup_bodies
+    out = []
+    n_chains = n_target // 12
+    for mode in ('eager', 'lazy'):
+        ctx = B200Context('x+y+z+w0', dtype=torch.float32, lazy=(mode == 'lazy'))
+        bodies, sets = setup_bodies(ctx, n_bodies=12)
+        big, bsets = replicate_chains(bodies, sets, n_chains)
+        big = big.copy(rate=big.rate + device_mv(ctx, ctx.subspace.bivector(), 12 * n_chains, 16, rank, scale=0.3))
+        big.rate.values
+        state = [big]
+
+        def step():
+            new = state[0].integrate(1 / 200, bsets)
+            new.motor.values, new.rate.values
+            state[0] = new
+        l0 = rt.launch_count()
+        step()
+        launches = rt.launch_count() - l0
+        ms = time_steps(step, 5, 2)
+        n = 12 * n_chains
+        out.append({'config': f'supplementary: reference-style Body.integrate (unchanged formulas, {mode}: {launches} generated kernels per sub-step), fp32, {n} bodies',
+                    'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': 0, 'achieved_gbs': 0.0, 'frac_of_hbm_peak': 0.0,
+                    'kernel_launches_per_step': launches})
+        del big, bsets, state
+        torch.cuda.empty_cache()
     return out
 
 
