@@ -471,6 +471,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stderr: stdout carries ONE JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     peak, peak_src = measured_peaks()
     n = args.points
