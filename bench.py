@@ -471,9 +471,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stderr: stdout carries ONE JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # NCCL prints a version banner on stdout when the communicator is created; stdout must carry ONE JSON line, so
+        # file descriptor 1 points at stderr while the process group and its first collective come up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     peak, peak_src = measured_peaks()
     n = args.points
     ctx = B200Context((3, 0, 1), dtype=torch.float32, device=f'cuda:{local}')
