@@ -7,6 +7,7 @@ test tier can check orchestration logic numerically (broadcasting, gather/scatte
 data without a GPU.  The arithmetic is that of the IR, op by op in the context dtype (= FAITHFUL semantics).
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -79,4 +80,5 @@ def emulated_context(algebra, dtype=torch.float64, mode='faithful'):
     """A context on CPU tensors for use inside `emulate_launches()`."""
     ctx = B.B200Context(algebra, dtype=dtype, device='cpu', mode=mode, compile_only=True)
     ctx.compile_only = False     # every launch site is patched; host-side torch set-up work (e.g. inverse()) runs for real
+    ctx.lazy = os.environ.get('NGB200_TEST_LAZY', '0') == '1'      # rerun any CPU-tier test under automatic fusion
     return ctx

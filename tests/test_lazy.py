@@ -167,3 +167,13 @@ def test_autograd_through_a_lazily_fused_chain(where):
             grads[name] = (b.grad.detach().cpu().numpy(), launches_fwd, counter['n'] - launches_fwd)
         assert np.allclose(grads['lazy'][0], grads['eager'][0], atol=1e-12)
         assert grads['lazy'][1] == 1 and grads['lazy'][2] == 1           # one forward kernel, one backward kernel
+
+
+@pytest.mark.parametrize('which', ['test_bisect', 'test_motor_split', 'test_inverse_compare', 'test_study'])
+def test_reference_identities_also_hold_under_lazy_fusion(which, monkeypatch):
+    """The ported reference tests are written against the plain API; with NGB200_TEST_LAZY=1 the emulated contexts
+    record and fuse everything, and the identities must still hold (every CPU-tier file can be rerun this way)."""
+    import test_reference_identities as T
+    monkeypatch.setenv('NGB200_TEST_LAZY', '1')
+    descr = {'test_bisect': (3, 0, 1), 'test_motor_split': (3, 0, 1), 'test_inverse_compare': (2, 1, 0), 'test_study': (4, 0, 1)}[which]
+    getattr(T, which)(descr, 'cpu')
