@@ -13,8 +13,14 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
-@pytest.fixture(scope='session', autouse=True)
-def _built_library():
-    """The C-ABI library must exist for every test (CPU tests compile kernels with NVRTC, no launches)."""
-    from numga_b200 import build
-    build.build(verbose=False)
+def _build_library():
+    """The C-ABI library must exist before any test module imports the package (CPU tests compile kernels with NVRTC,
+    no launches).  The build script is loaded by path: importing `numga_b200` needs the library it produces."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_numga_b200_build', os.path.join(ROOT, 'numga_b200', 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build(verbose=False)
+
+
+_build_library()
