@@ -7,8 +7,8 @@ rows = list(csv.reader(open('gpurun_out/lazy_launches.csv')))
 hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 H = rows[hdr]
 seq = [(dict(zip(H, r))['Kernel Name'][:300], float(dict(zip(H, r))['Metric Value'])) for r in rows[hdr + 1:]]
-last = seq[-260:]   # roughly the last sub-steps
+last = seq[-60:]   # roughly the last sub-steps
 agg = collections.Counter(); cnt = collections.Counter()
 for n, t in last: agg[n] += t; cnt[n] += 1
-for n, t in agg.most_common(8): print(f'{t/1e3:10.1f} us total {cnt[n]:4d} x  {n[60:260]}')
+for n, t in agg.most_common(8): print(f'{t/1e3:10.1f} us total {cnt[n]:4d} x  {n[:46] + ' ' + n[60:150]}')
 PY

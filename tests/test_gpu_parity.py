@@ -332,3 +332,19 @@ def test_partially_broadcast_operands_are_addressed_in_the_kernel(shapes):
     modes = list(ctx.engine.cache.values())[-1].program.in_mode
     regular = shapes not in [((2, 5, 3), (2, 1, 3)), ((3, 1, 7), (1, 4, 1))]
     assert (rt.TILED in modes) == regular
+
+
+@pytest.mark.parametrize('name,log2n', [('pga3_gp_motor', 20), ('pga3_sandwich_point_bcast', 20), ('pga3_normalized', 20),
+                                        ('pga3_sandwich_bivector', 20), ('pga3_roundtrip', 18), ('cga3_gp_full', 16)])
+def test_parity_batch_of_a_million_items_vs_oracle(name, log2n):
+    """SURVEY.md 8d parity batch: 2^20 seeded items per product config (fewer where the dense-einsum oracle is slow)
+    through the fast fp32 path, max over items of ||gpu - oracle||inf / ||oracle||inf <= 1e-5 (chains: 2e-3)."""
+    case = [c for c in CASES if c[0] == name][0]
+    n = (1 << log2n) + 1
+    ctx = _ctx(case[1], np.float32, 'fast')
+    widths = [len(getattr(ctx.subspace, s)()) for s, _ in case[2]]
+    ins = case_inputs(case, np.float32, batch=n, seed=log2n)(widths)
+    want = _oracle(case, np.float32, ins).values
+    got = _run(case, ctx, ins, 'jit').numpy()
+    assert got.shape == want.shape
+    assert _rel_err(got, want) < (CHAIN_TOL[np.float32] if 'roundtrip' in name else TOL[np.float32])
