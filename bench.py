@@ -542,7 +542,7 @@ def run_ours(args):
         host_p[:, i:i + chunk] = p.values[i:i + chunk].T.cpu().numpy()
     ins = [(hR.value, 1, 0), (hin.value, e2e_n, 1)]
     outs = [(hout.value, e2e_n, 1)]
-    e2e_steps = max(1, min(args.steps, 4))
+    e2e_steps = max(1, min(args.steps, 10))
     prog.run_host(ins, outs, e2e_n, device=local)
     if dist is not None:
         dist.barrier()
