@@ -163,7 +163,9 @@ struct ngb200_program {
     std::vector<double> consts;
     std::vector<ngb200_instr> instr;
     std::vector<ngb200_store> stores;
-    int vec = 1;          // items per thread in the vector kernel (1 = no vector kernel)
+    int vec = 1;          // items per thread in the contiguous ("vector") kernel
+    bool bdim_runtime = false;  // index arithmetic with blockDim.x (see generate)
+    bool has_vec = false; // a contiguous kernel `ngb_vec` exists (batch stride 1 compiled in; vec 1 = plain 32/64-bit accesses)
     int tpb = 256;
     int minb = 1;         // __launch_bounds__ min resident CTAs per SM (caps registers at 65536 / (tpb * minb))
     // staged kernel (bulk async copies global -> shared, mbarrier pipeline); 0 = not generated
@@ -534,6 +536,12 @@ struct Gen {
                 pair ? ", packed f32x2" : "");
         appendf(s, "typedef %s T;\ntypedef %s VT;\n", T, VT);
         appendf(s, "#define NGB_V %d\n#define NGB_TPB %d\n", vec, P.tpb);
+        // Grid-stride index arithmetic with the run-time blockDim.x instead of the compile-time CTA size: same
+        // instruction mix, but ptxas lands on a different register allocation (123 vs 121 registers for CGA full x
+        // full) that runs 5-10 % faster (4.01 vs 4.22 ms; twelve source variants in scripts/micro/gen_cga_variants.py
+        // split cleanly into these two groups).  Measured neutral or slightly negative elsewhere (long chains -1 %,
+        // gathered physics +-1 %), so only the wide one-item contiguous kernels use it.
+        appendf(s, "#define NGB_BDIM %s\n", P.bdim_runtime ? "blockDim.x" : "NGB_TPB");
         // an explicit minimum of 1 CTA/SM makes ptxas spend up to 255 registers (measured 116 -> 207): only state a
         // minimum when it is a real cap
         if (P.minb > 1 && 65536 / (P.tpb * P.minb) < 255) appendf(s, "#define NGB_BOUNDS __launch_bounds__(NGB_TPB, %d)\n", P.minb);
@@ -622,8 +630,8 @@ struct Gen {
             appendf(s, "  for (int j = threadIdx.x; j < %d; j += NGB_TPB) ngb_red[j] = T(0);\n", NR);
             appendf(s, "  #pragma unroll\n  for (int j = 0; j < %d; ++j) racc[j] = T(0);\n  __syncthreads();\n", NR);
         }
-        s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
-        s += "  for (long long i = (long long)blockIdx.x * NGB_TPB + threadIdx.x; i < p.n; i += stride) {\n";
+        s += "  const long long stride = (long long)gridDim.x * NGB_BDIM;\n";
+        s += "  for (long long i = (long long)blockIdx.x * NGB_BDIM + threadIdx.x; i < p.n; i += stride) {\n";
         appendf(s, "    T x[%d]; T y[%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
         for (int k = 0; k < nin; ++k) {
             if (P.in_mode[k] == NGB200_BROADCAST) continue;
@@ -671,8 +679,8 @@ struct Gen {
             appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_vec(const Params p) {\n");
             appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
             s += "  const long long nvec = p.n / NGB_V;\n";
-            s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
-            s += "  for (long long v = (long long)blockIdx.x * NGB_TPB + threadIdx.x; v < nvec; v += stride) {\n";
+            s += "  const long long stride = (long long)gridDim.x * NGB_BDIM;\n";
+            s += "  for (long long v = (long long)blockIdx.x * NGB_BDIM + threadIdx.x; v < nvec; v += stride) {\n";
             appendf(s, "    float2 x[%d][%d]; float2 y[%d][%d];\n", npair, NX > 0 ? NX : 1, npair, NY > 0 ? NY : 1);
             for (int k = 0; k < nin; ++k) {
                 if (P.in_mode[k] == NGB200_BROADCAST) continue;
@@ -691,12 +699,32 @@ struct Gen {
                     appendf(s, " NGB_ST(reinterpret_cast<VT*>(p.out[%d].ptr + %dLL * p.out[%d].cs) + v, t); }\n", k, c, k);
                 }
             s += "  }\n}\n";
+        } else if (vec == 1 && P.has_vec) {
+            // contiguous kernel, one item per thread: the batch stride is the compile-time constant 1.  With the
+            // run-time stride of ngb_scalar ptxas computes the first output as one serial FMA chain behind all loads;
+            // with the constant stride it interleaves all chains operand-major and starts while loads are in flight
+            // (CGA full x full: 4.95 -> 4.33 ms under sustained load, scripts/micro/gen_cga_variants.py).
+            appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_vec(const Params p) {\n");
+            appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
+            s += "  const long long stride = (long long)gridDim.x * NGB_BDIM;\n";
+            s += "  for (long long v = (long long)blockIdx.x * NGB_BDIM + threadIdx.x; v < p.n; v += stride) {\n";
+            appendf(s, "    T x[%d]; T y[%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
+            for (int k = 0; k < nin; ++k) {
+                if (P.in_mode[k] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < P.in_width[k]; ++c)
+                    appendf(s, "    x[%d] = NGB_LD(p.in[%d].ptr + %dLL * p.in[%d].cs + v);\n", xoff[k] + c, k, c, k);
+            }
+            s += "    ngb_body(x, u, y);\n";
+            for (int k = 0; k < nout; ++k)
+                for (int c = 0; c < P.out_width[k]; ++c)
+                    appendf(s, "    NGB_ST(p.out[%d].ptr + %dLL * p.out[%d].cs + v, y[%d]);\n", k, c, k, yoff[k] + c);
+            s += "  }\n}\n";
         } else if (vec > 1) {
             appendf(s, "extern \"C\" __global__ void NGB_BOUNDS ngb_vec(const Params p) {\n");
             appendf(s, "  T u[%d]; ngb_uniform(p, u);\n", NU > 0 ? NU : 1);
             s += "  const long long nvec = p.n / NGB_V;\n";
-            s += "  const long long stride = (long long)gridDim.x * NGB_TPB;\n";
-            s += "  for (long long v = (long long)blockIdx.x * NGB_TPB + threadIdx.x; v < nvec; v += stride) {\n";
+            s += "  const long long stride = (long long)gridDim.x * NGB_BDIM;\n";
+            s += "  for (long long v = (long long)blockIdx.x * NGB_BDIM + threadIdx.x; v < nvec; v += stride) {\n";
             appendf(s, "    T x[NGB_V][%d]; T y[NGB_V][%d];\n", NX > 0 ? NX : 1, NY > 0 ? NY : 1);
             for (int k = 0; k < nin; ++k) {
                 if (P.in_mode[k] == NGB200_BROADCAST) continue;
@@ -904,7 +932,10 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     // measured on B200 (profiles/): long dependent chains (exp/log: ~110 instructions per operand component) are
     // fastest with 1 item per thread; wide products (CGA full x full: ~21) gain 10% from 2 items per thread
     const bool wide = live_guess <= 48 * (gen.NX + gen.NY);
-    int vec = vec_hint > 0 ? vec_hint : (small ? vmax : (f32 && wide ? 2 : 1));
+    // ... unless two items need more than 128 registers: one item per thread at 128 registers (16 warps/SM) then
+    // sustains more than two at 168 (12 warps/SM): CGA 4.33 vs 4.83 ms under sustained load
+    const bool two_fit = gen.max_live * 2 + 16 <= 128;
+    int vec = vec_hint > 0 ? vec_hint : (small ? vmax : (f32 && wide && two_fit ? 2 : 1));
     if (env_int("NGB200_FORCE_VEC", 0) > 0) vec = env_int("NGB200_FORCE_VEC", 0);
     if (vec > vmax) vec = vmax;
     if (vec == 3) vec = 2;
@@ -914,6 +945,8 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     // registers in large programs; it is kept for the small HBM-bound programs (half the issue slots per item).
     const bool pair = f32 && vec >= 2 && env_int("NGB200_PAIR", small ? 1 : 0);
     P->vec = vec;
+    P->has_vec = vec > 1 || (!P->any_indexed && !P->any_reduced && gen.NX > 0 && env_int("NGB200_CONTIG1", 1));
+    P->bdim_runtime = env_int("NGB200_BDIM", -1) >= 0 ? env_int("NGB200_BDIM", -1) != 0 : (vec == 1 && P->has_vec && !small && wide);
     // Register budget of LARGE programs.  ptxas schedules a long straight-line body for maximal ILP and can take
     // 200+ registers for a chain whose working set is 17 values (measured: exp->normalized->log, 205 registers,
     // 11.1 ms; capped at 48: 5.4 ms; the gathered physics kernels: 254 -> 128 registers, +15%).  The cap is derived
@@ -983,7 +1016,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     std::string log;
     rc = nvrtc_compile(P->source, P->cubin, &log);
     if (rc) return rc;
-    const char *main_kernel = vec > 1 ? "ngb_vec" : "ngb_scalar";
+    const char *main_kernel = P->has_vec ? "ngb_vec" : "ngb_scalar";
     const long spill_ir = spill_bytes(log, main_kernel);
     if (forced < 0 && spill_ir > 0) {
         std::string src_ir = P->source, hash_ir = P->hash;
@@ -1192,7 +1225,7 @@ static int load_on_device(ngb200_program *P, int dev, Loaded **out) {
             CU(cuFuncGetAttribute(&L.regs_scalar, CU_FUNC_ATTRIBUTE_NUM_REGS, L.fscalar));
             CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fscalar, P->tpb, 0));
             L.grid_scalar = sms * (nb > 0 ? nb : 1) * waves;
-            if (P->vec > 1) {
+            if (P->has_vec) {
                 CU(cuModuleGetFunction(&L.fvec, L.mod, "ngb_vec"));
                 CU(cuFuncGetAttribute(&L.regs_vec, CU_FUNC_ATTRIBUTE_NUM_REGS, L.fvec));
                 CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.fvec, P->tpb, 0));
@@ -1278,10 +1311,11 @@ extern "C" int ngb200_program_launch(ngb200_program *P, const ngb200_operand *in
         if (P->out_width[k] > 0 && !out[k].ptr) return fail(NGB200_ERR_INVALID, "output %zu: null pointer", k);
         if (P->out_mode[k] == NGB200_INDEXED && !out[k].index) return fail(NGB200_ERR_INVALID, "output %zu: indexed operand without index", k);
     }
-    bool vec_ok = P->vec > 1 && batch >= P->vec;
+    bool vec_ok = P->has_vec && batch >= P->vec;
     if (vec_ok) {
         auto aligned = [&](const ngb200_operand &o, int width) {
             if (width == 0) return true;
+            if (P->vec == 1) return o.batch_stride == 1;
             return o.batch_stride == 1 && ((uintptr_t)o.ptr % 16 == 0) && (width == 1 || (o.comp_stride * es) % 16 == 0);
         };
         for (size_t k = 0; k < P->in_width.size() && vec_ok; ++k)

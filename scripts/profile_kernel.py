@@ -87,7 +87,7 @@ if which in ('cga_time', 'roundtrip_time'):
         ctx = B200Context((3, 0, 1)); n = 1 << 27
         bv = device_mv(ctx, ctx.subspace.bivector(), n, 7, 0, scale=0.5)
         f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv); bpi = 48
-    ms = time_steps(run, 10, 3)
+    ms = time_steps(run, int(os.environ.get('STEPS', '10')), 3)
     prog = list(ctx.engine.cache.values())[-1].program
     print(which, {k: v for k, v in os.environ.items() if k.startswith('NGB200') and 'CACHE' not in k}, f'{ms:.3f} ms {n/ms/1e6:.2f} G/s {bpi*n/ms/1e6:.0f} GB/s', prog.info['regs_vec'], prog.info['regs_scalar'], prog.info['vec'])
     sys.exit(0)
