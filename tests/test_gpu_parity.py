@@ -201,6 +201,54 @@ def test_raw_cabi_strided_aos_and_host_path():
     assert np.array_equal(res_s, res)
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_raw_cabi_gather_scatter_unit_and_strided_batch(dtype):
+    """INDEXED operands through ngb200_program_launch: out[dst[i]] = a[src[i]] * b[i] (motor product), once with
+    structure-of-arrays operands (batch stride 1: the `ngb_scalar_u` kernel with the stride compiled in) and once with
+    array-of-structs operands (batch stride = width: the generic `ngb_scalar`).  Both must be bit-identical."""
+    from numga_b200 import runtime as rt
+    from numga_b200.algebra import Algebra
+    A = Algebra.from_pqr(3, 0, 1)
+    M = A.subspace.even_grade()
+    op = A.operator.product(M, M)
+    ctx = _ctx((3, 0, 1), dtype, 'faithful')
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    terms = np.concatenate([op.index, op.coeff[:, None]], axis=1)
+    plain = rt.Program.from_terms(terms, [8, 8], 8, rt.F32 if dtype == np.float32 else rt.F64, flags=rt.FAITHFUL)
+    n, m = 70001, 5000
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((m, 8)).astype(dtype)
+    b = rng.standard_normal((n, 8)).astype(dtype)
+    src = rng.integers(0, m, n)
+    dst = rng.permutation(n)
+    # reference: gather on the host, plain kernel, scatter on the host
+    ad, bd = torch.as_tensor(a[src].T.copy(), device='cuda'), torch.as_tensor(b.T.copy(), device='cuda')
+    ref = torch.empty((8, n), dtype=tdt, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    plain.launch([(ad.data_ptr(), n, 1), (bd.data_ptr(), n, 1)], [(ref.data_ptr(), n, 1)], n, st)
+    want = np.empty((n, 8), dtype)
+    want[dst] = ref.cpu().numpy().T
+    # gathered program: same IR with INDEXED modes
+    f = ctx.jit(lambda x, y: x * y)
+    Mc = ctx.subspace.even_grade()
+    av = ctx.multivector(values=torch.as_tensor(a, device='cuda'), subspace=Mc)
+    bv = ctx.multivector(values=torch.as_tensor(b, device='cuda'), subspace=Mc)
+    out = ctx.multivector(values=torch.zeros((n, 8), dtype=tdt, device='cuda'), subspace=Mc)
+    srcd, dstd = torch.as_tensor(src, device='cuda'), torch.as_tensor(dst, device='cuda')
+    f(av.indexed(srcd), bv, out=out.indexed(dstd))
+    got_soa = out.values.cpu().numpy()
+    assert np.array_equal(got_soa, want)
+    prog = [v.program for k, v in ctx.engine.cache.items() if rt.INDEXED in v.program.in_mode][-1]
+    assert 'ngb_scalar_u' in prog.source
+    # the same compiled program on array-of-structs buffers (batch stride 8, component stride 1)
+    a_aos, b_aos = torch.as_tensor(a, device='cuda').contiguous(), torch.as_tensor(b, device='cuda').contiguous()
+    o_aos = torch.zeros((n, 8), dtype=tdt, device='cuda')
+    prog.launch([(a_aos.data_ptr(), 1, 8, srcd.data_ptr()), (b_aos.data_ptr(), 1, 8)],
+                [(o_aos.data_ptr(), 1, 8, dstd.data_ptr())], n, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(o_aos.cpu().numpy(), want)
+
+
 def test_fill_normal_is_deterministic_and_normal():
     from numga_b200 import runtime as rt
     n = 1 << 22
