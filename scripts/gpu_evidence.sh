@@ -14,6 +14,6 @@ ncu --set full --clock-control none --import-source on -k 'regex:ngb_(vec|scalar
 echo "ncu $which rc=$?"
 done
 python scripts/profile_kernel.py physics_time > gpurun_out/plain_physics.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:ngb_(vec|scalar)' -s 30 -c 6 -o gpurun_out/prof_physics -f python scripts/profile_kernel.py physics_time > gpurun_out/ncu_physics_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:ngb_(vec|scalar|scalar_u)' -s 30 -c 6 -o gpurun_out/prof_physics -f python scripts/profile_kernel.py physics_time > gpurun_out/ncu_physics_full.log 2>&1
 echo "ncu physics rc=$?"
 ls -la gpurun_out/*.ncu-rep
