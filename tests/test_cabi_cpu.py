@@ -72,6 +72,29 @@ def test_generated_sass_uses_128bit_global_accesses(tmp_path):
         rt.check(rt.lib.ngb200_set_cache_dir(b''))
 
 
+def test_kernel_variants_per_program_class():
+    """Which kernels the generator emits ('Kernels'): small programs a 128-bit vector kernel; wide programs
+    whose two items do not fit in 128 registers a ONE-item contiguous kernel (batch stride compiled in, blockDim.x
+    index arithmetic); gathered programs a second scalar kernel with the batch stride compiled in."""
+    pga, cga = Algebra.from_pqr(3, 0, 1), Algebra.from_pqr(4, 1, 0)
+    M, F = pga.subspace.even_grade(), cga.subspace.full()
+    small = rt.Program.from_terms(_terms(pga.operator.product(M, M)), [8, 8], 8, rt.F32)
+    assert small.info['vec'] == 4 and 'float4' in small.source and 'ngb_scalar_u' not in small.source
+    wide = rt.Program.from_terms(_terms(cga.operator.product(F, F)), [32, 32], 32, rt.F32)
+    src = wide.source
+    assert wide.info['vec'] == 1 and 'ngb_vec(const Params p)' in src and '#define NGB_BDIM blockDim.x' in src
+    assert 'x[0] = NGB_LD(p.in[0].ptr + 0LL * p.in[0].cs + v);' in src            # no run-time batch stride
+    assert 'ngb_scalar(const Params p)' in src                                    # strided fallback still there
+    # gathered: out[i] = a[index[i]] + b[i]
+    instr = [(rt.OP_INPUT, 0, 0, 0), (rt.OP_INPUT, 1, 0, 0), (rt.OP_ADD, 0, 1, 0)]
+    gathered = rt.Program.from_ir(rt.F32, rt.FAST, [1, 1], [rt.INDEXED, rt.VARYING], [1], [rt.VARYING], 0, [], instr, [(0, 0, 2)])
+    src = gathered.source
+    assert 'ngb_scalar_u(const Params p)' in src and 'ngb_vec' not in src
+    generic, unit = src.split('ngb_scalar_u(const Params p)')
+    assert 'p.in[0].index[i] NGB_BS(p.in[0].bs)' in generic and '#define NGB_BS(b) * (b)' in generic
+    assert unit.count('#define NGB_BS') == 0 and '#define NGB_BS(b) \n' in generic.split('ngb_scalar(const Params p)')[1]
+
+
 def test_bad_descriptions_are_rejected_with_a_message():
     with pytest.raises(rt.NGB200Error, match='out of range'):
         rt.Program.from_terms([[9, 0, 0, 1]], [8, 8], 8, rt.F32)
