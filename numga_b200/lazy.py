@@ -242,130 +242,7 @@ class LazyEngine:
     def _realize_unrolled(self, targets, out):
         """A batch [k, *rest] with small k whose slices share sub-expressions (a constraint acting on its two bodies):
         ONE kernel over the [*rest] items computes all k slices, the shared part once per item -- the arrangement a
-        hand-fused kernel would use -- instead of k * prod(rest) items that each recompute it.
-
-        The recorded DAG is walked ONCE; the k copies of the operations that carry the leading axis are made inside
-        the traced (hence cached) replay function, on the k views of every leaf that carries it.  (The first version
-        rebuilt the DAG slice by slice in python on every call -- `_realize_unrolled_sliced`, kept for the shapes
-        this walk does not cover -- which was a quarter of the host time of a reference-style physics step.)"""
-        from numga_b200.backend import Indexed, soa_empty
-        ctx = self.context
-        bshape = targets[0].shape
-        k, rest, rank = bshape[0], bshape[1:], len(bshape)
-        order, fns, full, index = [], [], [], {}
-        leaves, slots, leaf_index = [], [], {}          # flat kernel arguments; per original leaf: (start, per_slice)
-
-        class Unsupported(Exception):
-            pass
-
-        def leaf(key, views):
-            if key not in leaf_index:
-                leaf_index[key] = len(slots)
-                slots.append((len(leaves), len(views) > 1))
-                leaves.extend(views)
-            return leaf_index[key]
-
-        def carries(shape):
-            """0: no leading axis (shared by the slices), 1: leading axis of size 1 (shared), k: one value per slice"""
-            if len(shape) < rank:
-                return 0
-            if len(shape) > rank or shape[0] not in (1, k):
-                raise Unsupported
-            return shape[0] if k > 1 else 0
-
-        def visit(mv):
-            node = mv._node
-            if id(node) in index:
-                return index[id(node)]
-            refs = []
-            for a, d in zip(node.args, node.static):
-                if d[0] == 'mv':
-                    if isinstance(a, self.cls) and a._values is None and a._node.key == 'gather':
-                        base, idx = a._node.args
-                        c = carries(a.shape)
-                        if c == k and k > 1 and a.shape[1:] == rest:
-                            refs.append(('l', leaf(id(a), [Indexed(base, idx[j]) for j in range(k)])))
-                        elif c == 1 and a.shape[1:] == rest:
-                            refs.append(('l', leaf(id(a), [Indexed(base, idx[0])])))
-                        elif c == 0 and a.shape == rest:
-                            refs.append(('l', leaf(id(a), [a._indexed])))
-                        elif c == 0 and len(a.shape) < len(rest) and rest[len(rest) - len(a.shape):] == a.shape:
-                            refs.append(('l', leaf(id(a), [self._expanded(a, rest)])))
-                        else:
-                            raise Unsupported
-                    elif isinstance(a, self.cls) and a._values is None:
-                        refs.append(('n', visit(a)))
-                    else:
-                        c = carries(a.shape)
-                        if c == k and k > 1:
-                            refs.append(('l', leaf(id(a), [self._concrete_slice(a, j) for j in range(k)])))
-                        elif c == 1:
-                            refs.append(('l', leaf(id(a), [self._concrete_slice(a, 0)])))
-                        else:
-                            refs.append(('l', leaf(id(a), [a])))
-                elif d[0] == 'param':
-                    slots.append((len(leaves), False))
-                    leaves.append(float(a))
-                    refs.append(('l', len(slots) - 1))
-                elif d[0] == 'const':
-                    refs.append(('c', d[1]))
-                else:
-                    refs.append(('s', d[1]))
-            index[id(node)] = len(order)
-            order.append((node.key, tuple(refs)))
-            fns.append(node.fn)
-            full.append(carries(mv.shape) == k and k > 1)
-            return index[id(node)]
-
-        try:
-            for t in targets:
-                visit(t)
-        except Unsupported:
-            return self._realize_unrolled_sliced(targets, out)
-        n_slices = k if k > 1 else 1
-        dests, holders = [], []
-        for n, t in enumerate(targets):
-            if out is not None:
-                dest = out[n]
-                assert isinstance(dest, Indexed), 'unrolled scatter needs an indexed destination'
-                dests.extend(Indexed(dest.target, dest.index[j]) for j in range(k))
-            else:
-                holder = ctx.mvtype(ctx, t.subspace, soa_empty(len(t.subspace), t.shape, ctx.dtype, ctx.device))
-                dests.extend(ctx.mvtype(ctx, t.subspace, holder.values[j]) for j in range(k))
-                holders.append(holder)
-        outs = tuple(index[id(t._node)] for t in targets)
-        frozen_slots, frozen_full = tuple(slots), tuple(full)
-        structure = ('unrolled', k, tuple(order), frozen_full, frozen_slots, outs)
-
-        def replay(*lv):
-            shared = [None] * len(order)
-            sliced = [[None] * len(order) for _ in range(n_slices)]
-
-            def arg(r, j):
-                kind, x = r
-                if kind == 'n':
-                    return sliced[j][x] if frozen_full[x] else shared[x]
-                if kind == 'l':
-                    start, per_slice = frozen_slots[x]
-                    return lv[start + (j if per_slice else 0)]
-                return x
-
-            for n, ((key, refs), fn) in enumerate(zip(order, fns)):
-                if frozen_full[n]:
-                    for j in range(n_slices):
-                        sliced[j][n] = fn(*[arg(r, j) for r in refs])
-                else:
-                    shared[n] = fn(*[arg(r, 0) for r in refs])
-            result = tuple((sliced[j][o] if frozen_full[o] else shared[o]) for o in outs for j in range(k))
-            return result[0] if len(result) == 1 else result
-
-        ctx.engine.call(('lazy', structure), replay, tuple(leaves), out=tuple(dests))
-        if out is None:
-            for t, holder in zip(targets, holders):
-                t.values = holder.values
-
-    def _realize_unrolled_sliced(self, targets, out):
-        """The same result by rebuilding the DAG slice by slice on the python side (see `_realize_unrolled`)."""
+        hand-fused kernel would use -- instead of k * prod(rest) items that each recompute it."""
         from numga_b200.backend import Indexed, soa_empty
         ctx = self.context
         k = targets[0].shape[0]
