@@ -263,6 +263,32 @@ def test_fill_normal_is_deterministic_and_normal():
     assert torch.equal(half, a[n // 2:])          # shards of one stream: rank r fills its slice with offset
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_wide_program_on_offset_views_and_strided_inputs(dtype):
+    """CGA full x full (the one-item contiguous kernel: no alignment requirement) on views that start one item into
+    a structure-of-arrays buffer, and on array-of-structs inputs (run-time batch stride: the generic kernel).  All
+    three layouts must give the bit-identical result, equal to the oracle within the fp tolerance."""
+    ctx = _ctx((4, 1, 0), dtype)
+    F = ctx.subspace.full()
+    rng = np.random.default_rng(33)
+    n = 40003
+    a, b = rng.standard_normal((n + 1, 32)).astype(dtype), rng.standard_normal((n + 1, 32)).astype(dtype)
+    A, B_ = ctx.multivector(values=torch.as_tensor(a, device='cuda'), subspace=F), \
+        ctx.multivector(values=torch.as_tensor(b, device='cuda'), subspace=F)
+    whole = (A * B_).values.cpu().numpy()
+    view = (A[1:] * B_[1:]).values.cpu().numpy()                     # pointers offset by one element per row
+    assert A[1:].values.data_ptr() % 16 != 0 and A[1:].values.stride(0) == 1
+    assert np.array_equal(view, whole[1:])
+    aos = torch.as_tensor(a[1:], device='cuda').contiguous()
+    raw = ctx.mvtype(ctx, F, aos)                                    # array-of-structs storage, not converted
+    assert raw.values.stride(-1) == 1
+    strided = (raw * B_[1:]).values.cpu().numpy()
+    assert np.array_equal(strided, whole[1:])
+    octx = O.context((4, 1, 0), dtype)
+    want = (octx.multivector('full', a[1:]) * octx.multivector('full', b[1:])).values
+    assert _rel_err(view, want) < (1e-5 if dtype == np.float32 else 1e-12)
+
+
 # ---- size-independent properties at the BASELINE.json configuration sizes ----------------------------------
 def _device_mv(ctx, sub, n, seed, scale=1.0):
     from numga_b200 import runtime as rt
