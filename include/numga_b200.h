@@ -129,7 +129,7 @@ typedef struct ngb200_program ngb200_program;
 typedef struct ngb200_program_info {
     int32_t n_instr;      /* live instructions after dead-code elimination */
     int32_t n_uniform;    /* of which evaluated once per thread (broadcast-only) */
-    int32_t vec;          /* items per thread of the vectorised kernel */
+    int32_t vec;          /* items per thread of the contiguous kernel (4/2: 128/64-bit accesses; 1: plain accesses) */
     int32_t regs_vec;     /* registers per thread (0 until loaded on a device) */
     int32_t regs_scalar;
     int32_t cache_hit;    /* 1 if the cubin came from the on-disk cache */

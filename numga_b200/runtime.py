@@ -108,7 +108,8 @@ def _i32(seq):
 
 
 class Program:
-    """A compiled straight-line program (one kernel pair: 128-bit vectorised + generic strided)."""
+    """A compiled straight-line program (one cubin: a contiguous kernel, vectorised where that pays, + a generic
+    strided / gather-scatter kernel)."""
 
     def __init__(self, handle, in_width, in_mode, out_width, out_mode, n_params, dtype):
         self.handle = C.c_void_p(handle)
