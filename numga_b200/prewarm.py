@@ -61,7 +61,7 @@ def _run(ctx, fn, specs, batch=8):
 def jobs():
     """(kind, argument) pairs; every job is independent of the others."""
     _paths()
-    out = [('bench', None)]
+    out = [('bench', None), ('gather', None)]
     out += [('physics', (dt, mode)) for dt in ('float32', 'float64') for mode in ('fast', 'faithful')]
     if os.path.isdir(os.path.join(ROOT, 'tests')):
         from cases import CASES
@@ -83,6 +83,19 @@ def run_job(job):
     if kind == 'bench':
         for ctx, fn, specs in bench_programs(ctx_of):
             _run(ctx, fn, specs)
+    elif kind == 'gather':
+        # gather / scatter through `indexed` operands and `out=` destinations (tests/test_gpu_parity.py)
+        import numpy as np
+        from numga_b200 import runtime as rt
+        for dtype in (torch.float32, torch.float64):
+            ctx = ctx_of((3, 0, 1), dtype, 'faithful')
+            M = ctx.subspace.even_grade()
+            a, b, o = (ctx.multivector(values=torch.zeros((8, 8), dtype=dtype), subspace=M) for _ in range(3))
+            idx = torch.arange(8)
+            ctx.jit(lambda x, y: x * y)(a.indexed(idx), b, out=o.indexed(idx))
+            op = ctx.algebra.operator.product(M, M)
+            terms = np.concatenate([op.index, op.coeff[:, None]], axis=1)
+            rt.Program.from_terms(terms, [8, 8], 8, rt.F32 if dtype == torch.float32 else rt.F64, flags=rt.FAITHFUL)
     elif kind == 'physics':
         # rigid-body physics (config 5): the generic per-method kernels and the six fused kernels of a sub-step
         from numga_b200.examples.physics import FusedStep, setup_bodies
