@@ -37,6 +37,9 @@ def _canonical(index, coeff, ncols):
     return index[keep], coeff[keep]
 
 
+_UIDS = {}          # structural key -> uid (see Operator.uid); entries are tiny and live for the process
+
+
 class Operator:
     """Sparse symbolic multilinear operator; `axes` = input subspaces + output subspace."""
 
@@ -61,6 +64,14 @@ class Operator:
         return Operator(self.axes if axes is None else axes, index, coeff)
 
     # ---- basic properties ----------------------------------------------------------------------
+    @cached_property
+    def uid(self):
+        """Small integer naming the CONTENT of this operator (axes + term table): equal operators share it, so
+        compiled-kernel caches keyed on it can neither collide after garbage collection recycles an address
+        (`id()`), nor miss for a structurally identical operator that was rebuilt."""
+        key = (self.axes, self.index.tobytes(), self.coeff.tobytes())
+        return _UIDS.setdefault(key, len(_UIDS))
+
     @property
     def arity(self):
         return len(self.axes) - 1

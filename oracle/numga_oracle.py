@@ -329,9 +329,33 @@ def is_degenerate(alg, x):                    # subspace.py:366-368
 # ------------------------------------------------------------------------------------------------
 # multivectors and execution                       (backend/numpy/{operator,multivector,context}.py)
 # ------------------------------------------------------------------------------------------------
+OTYPE = 'einsum'      # which of the reference's two numpy operator classes `apply` restates: 'einsum' | 'sparse'
+
+
+def apply_sparse(op, *mvs, order='F'):
+    """NumpySparseOperator.__call__ (backend/numpy/operator.py:143-160): per non-empty output row, python `sum`
+    over one `np.einsum(',...,...->...', coeff, x[..., i], y[..., j])` per non-zero term, terms in the
+    lexicographic (i, j, ..) order of `precompute_sparse` (operator/abstract.py:119-151)."""
+    assert all(m.blades == ax for m, ax in zip(mvs, op.axes)), 'subspace mismatch'
+    dtype = mvs[0].values.dtype
+    shape = np.broadcast_shapes(*(m.values.shape[:-1] for m in mvs)) + (len(op.out),)
+    out = np.zeros(shape, dtype=dtype, order=order)
+    expr = ',...' * op.arity + '->...'
+    kernel = op.kernel
+    for o in range(kernel.shape[-1]):
+        terms = [(ii, kernel[ii + (o,)]) for ii in itertools.product(*[range(n) for n in kernel.shape[:-1]])
+                 if kernel[ii + (o,)]]
+        if terms:
+            out[..., o] = sum(np.einsum(expr, c, *(m.values[..., i] for m, i in zip(mvs, ii)), optimize=True)
+                              for ii, c in terms)
+    return MV(mvs[0].alg, op.out, out)
+
+
 def apply(op, *mvs, order='F'):
     """out[..., c] = sum K[a, b, c] x[..., a] y[..., b]: ONE einsum with optimize=True into a
     zero-initialised output of the context's memory order      (backend/numpy/operator.py:117-132)"""
+    if OTYPE == 'sparse':
+        return apply_sparse(op, *mvs, order=order)
     assert all(m.blades == ax for m, ax in zip(mvs, op.axes)), 'subspace mismatch'
     dtype = mvs[0].values.dtype
     letters = 'abcdefgh'[:op.arity + 1]

@@ -67,7 +67,7 @@ def emulate_launches():
     def operator_call(self, *inputs):
         if any(isinstance(i, (B.SubSpace, B.TracedMultiVector)) for i in inputs) or len(self.output) == 0:
             return orig_op_call(self, *inputs)
-        return self.context.engine.call(('operator', id(self.operator)), lambda *xs: orig_op_call(self, *xs), inputs)
+        return self.context.engine.call(('operator', self.operator.uid), lambda *xs: orig_op_call(self, *xs), inputs)
 
     B.CompiledFunction.launch, B.B200Operator.__call__ = compiled_call, operator_call
     try:

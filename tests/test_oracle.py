@@ -79,3 +79,64 @@ def test_known_integer_answers():
     assert (p & ctx.multivector('antivector', [4, 3, 2, 1.0])).values.tolist() == [-5, -10, -15, -5, -10, -5]
     assert bv.commutator(ctx.multivector('bivector', np.arange(6, 0, -1.0))).values.tolist() == [7, -14, 7, -56, 0, 28]
     assert bv.dual().values.tolist() == [6, -5, 4, 3, -2, 1]
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_oracle_sparse_operator_variant(dtype):
+    """`O.OTYPE = 'sparse'` restates NumpySparseOperator (backend/numpy/operator.py:143-160), the second CPU baseline
+    of bench.py.  Checked here against the golden vectors of the reference: within rounding of the einsum operator on
+    every case (the two reference operators sum the same terms in different association), and bit-identical to
+    the reference's own NumpySparseOperator when generated in the build container (see tests/golden/make_golden.py
+    docstring: `python /tmp/mk_sparse.py`-style spot check recorded in DESIGN.md)."""
+    O.OTYPE = 'sparse'
+    try:
+        exact = 0
+        for name, pqr, specs, scale, fn in CASES:
+            ins, want, want_blades = golden_io.case_vectors(name, dtype)
+            ctx = O.context(pqr, dtype)
+            mvs = [ctx.multivector(sub, a) for (sub, _), a in zip(specs, ins)]
+            with np.errstate(all='ignore'):
+                got = fn(*mvs)
+            assert list(got.blades) == want_blades.tolist()
+            g = np.broadcast_to(got.values, want.shape)
+            ok = np.isfinite(want) & np.isfinite(g)
+            scale_ = np.abs(want[ok]).max() if ok.any() else 1.0
+            tol = 5e-3 if dtype == np.float32 else 1e-9
+            assert np.abs(g[ok] - want[ok]).max() <= tol * scale_, name
+            exact += bool(np.array_equal(g, want, equal_nan=True))
+        assert exact >= len(CASES) // 3
+    finally:
+        O.OTYPE = 'einsum'
+
+
+@pytest.mark.parametrize('tag,dtype', [('f64', np.float64), ('f32', np.float32)])
+def test_oracle_physics_bit_exact(tag, dtype):
+    """oracle/physics_oracle.py (the CPU restatement of numga/examples/physics/core.py used as config 5's CPU baseline
+    and parity checker) against the stage-by-stage states of the unmodified reference: bit-exact, both dtypes."""
+    import os
+    from oracle import physics_oracle as P
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'physics.npz'))
+    arrays = {k[len(tag) + 1:]: G[k] for k in G.files if k.startswith(tag + '/')}
+    bodies, sets = P.from_arrays(arrays, dtype, rate=arrays['start/rate'])
+    dt = 1 / 200
+    new = bodies.pre_integrate(dt)
+    assert np.array_equal(new.motor.values, arrays['pre/motor']) and np.array_equal(new.rate.values, arrays['pre/rate'])
+    for k, c in enumerate(sets):
+        new = c.apply(new, dt)
+        assert np.array_equal(new.motor.values, arrays[f'apply{k}/motor'])
+    new = new.post_integrate(bodies, dt)
+    assert np.array_equal(new.motor.values, arrays['post/motor']) and np.array_equal(new.rate.values, arrays['post/rate'])
+    for k, c in enumerate(sets):
+        new = c.v_apply(new, dt)
+        assert np.array_equal(new.rate.values, arrays[f'vapply{k}/rate'])
+    b = bodies
+    for step in range(1, 6):
+        b = b.integrate(dt, sets)
+        if step in (1, 2, 5):
+            assert np.array_equal(b.motor.values, arrays[f'step{step}/motor'])
+            assert np.array_equal(b.rate.values, arrays[f'step{step}/rate'])
+    # replicated chains evolve alike (block-diagonal constraints; numpy's einsum may pick another inner loop for
+    # another batch size, so this is equality to rounding, not bitwise)
+    big, bsets = P.from_arrays(arrays, dtype, n_chains=3, rate=arrays['start/rate'])
+    many = big.integrate(dt, bsets)
+    assert np.allclose(many.motor.values.reshape(3, 12, 8), arrays['step1/motor'][None], rtol=0, atol=1e-5 if tag == 'f32' else 1e-13)

@@ -122,3 +122,35 @@ def test_error_behaviour_matches_reference():
         ctx.trace(lambda x: x.motor_log(), S.vector())
     with pytest.raises(AttributeError):
         S.vector().no_such_operator
+
+
+def test_transient_operators_never_hit_a_stale_kernel():
+    """Regression (round-1 ADVICE, high): compiled-function caches were keyed on id() of operator objects nobody
+    kept alive, so a garbage-collected operator's address could be reused by a DIFFERENT operator with the same
+    argument subspaces, which then ran the stale kernel.  Keys are structural now (`Operator.uid`)."""
+    import gc
+    from cpu_emulation import emulate_launches, emulated_context
+    from numga_b200.backend import B200Operator
+    ctx = emulated_context((3, 0, 0), dtype=torch.float64)
+    V = ctx.subspace.vector()
+    sym = ctx.algebra.operator
+    a = ctx.multivector.vector(np.array([1.0, 2.0, 3.0]))
+    b = ctx.multivector.vector(np.array([0.5, -1.0, 2.0]))
+    an, bn = a.numpy(), b.numpy()
+    want_c = np.array([an[0] * bn[1] - an[1] * bn[0], an[0] * bn[2] - an[2] * bn[0], an[1] * bn[2] - an[2] * bn[1]])
+    want_a = np.array([an @ bn])
+    with emulate_launches():
+        for it in range(40):
+            if it % 2 == 0:
+                got = B200Operator(ctx, sym.commutator_product(V, V)).partial({0: a})(b)
+                assert got.subspace is ctx.subspace.bivector() and np.allclose(got.numpy(), want_c), (it, got.numpy())
+            else:
+                got = B200Operator(ctx, sym.anti_commutator_product(V, V)).partial({0: a})(b)
+                assert got.subspace is ctx.subspace.scalar() and np.allclose(got.numpy(), want_a), (it, got.numpy())
+            del got
+            gc.collect()
+    # structurally equal operators share one uid, different ones never do
+    assert sym.commutator_product(V, V).uid != sym.anti_commutator_product(V, V).uid
+    from numga_b200.operator import Operator
+    op = sym.commutator_product(V, V)
+    assert Operator(op.axes, op.index.copy(), op.coeff.copy()).uid == op.uid
