@@ -146,48 +146,161 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU side: the oracle on the host cores
+# CPU side: the oracle (port of the reference's numpy backend) on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-_W = {}
+# Per configuration: items per worker per step for the reference's two numpy operator classes
+# (NumpyEinsumOperator = the default, NumpySparseOperator; numga/backend/numpy/operator.py:102-160).  Sized so that
+# one step is ~0.05-0.8 s on one core; the config sizes themselves (2^20 - 2^28) would take minutes to hours, numpy
+# is single-threaded and the work is linear in the batch, so throughput is reported per item.
+CPU_SAMPLES = {
+    'cfg1': {'einsum': 1 << 18, 'sparse': 1 << 18},
+    'cfg2': {'einsum': 1 << 22, 'sparse': 1 << 17},
+    'cfg3_f32': {'einsum': 1 << 14, 'sparse': 1 << 14},
+    'cfg3_f64': {'einsum': 1 << 14, 'sparse': 1 << 14},
+    'cfg4': {'einsum': 1 << 12, 'sparse': 1 << 13},
+    'cfg5_f32': {'einsum': 12 * 256, 'sparse': 12 * 256},
+    'cfg5_f64': {'einsum': 12 * 256, 'sparse': 12 * 256},
+}
+PHYSICS_DT = 1 / 200
 
 
-def _cpu_worker_init(n_points, seed):
+def physics_arrays(tag):
+    """Set-up state of the 12-body chain exactly as the reference's `setup_bodies` produces it (committed fixture,
+    generated from the unmodified reference by tests/golden/make_golden_physics.py)."""
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'physics.npz'))
+    return {k[len(tag) + 1:]: G[k] for k in G.files if k.startswith(tag + '/')}
+
+
+def cpu_workload(cfg, otype, n, seed):
+    """One pass of configuration `cfg`'s hot path over n items with the oracle; returns (step, inputs, result)."""
     from oracle import numga_oracle as O
-    alg = O.Algebra((3, 0, 1))
+    O.OTYPE = otype
     rng = np.random.default_rng(seed)
-    _W['R'] = O.MV.make(alg, 'even_grade', rng.standard_normal(8), np.float32)
-    _W['p'] = O.MV.make(alg, 'antivector', rng.standard_normal((n_points, 4)), np.float32)
-    _W['R'] >> _W['p']          # builds and caches the integer tables
+    if cfg == 'cfg1':
+        c = O.context((3, 0, 1), np.float32)
+        a, b = (c.multivector('even_grade', rng.standard_normal((n, 8))) for _ in range(2))
+        return lambda: a * b
+    if cfg == 'cfg2':
+        c = O.context((3, 0, 1), np.float32)
+        R = c.multivector('even_grade', rng.standard_normal(8))
+        p = c.multivector('antivector', rng.standard_normal((n, 4)))
+        return lambda: R >> p
+    if cfg.startswith('cfg3'):
+        c = O.context((3, 0, 1), np.float32 if cfg.endswith('f32') else np.float64)
+        bv = c.multivector('bivector', 0.5 * rng.standard_normal((n, 6)))
+        return lambda: bv.exp().normalized().motor_log()
+    if cfg == 'cfg4':
+        c = O.context((4, 1, 0), np.float32)
+        x, y = (c.multivector('multivector', rng.standard_normal((n, 32))) for _ in range(2))
+        return lambda: x * y
+    if cfg.startswith('cfg5'):
+        from oracle import physics_oracle as P
+        tag = cfg[-3:]
+        arrays = physics_arrays(tag)
+        chains = max(1, n // 12)
+        rate = np.tile(arrays['init/rate'], (chains, 1)) + 0.3 * rng.standard_normal((12 * chains, 6))
+        bodies, sets = P.from_arrays(arrays, np.float32 if tag == 'f32' else np.float64, n_chains=chains, rate=rate)
+        return lambda: bodies.integrate(PHYSICS_DT, sets)
+    raise KeyError(cfg)
 
 
-def _cpu_worker_step(_):
-    t = time.perf_counter()
-    out = _W['R'] >> _W['p']
-    return time.perf_counter() - t, float(out.values[0, 0])
+def _farm_worker(conn, cpu):
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except Exception:
+        pass
+    sys.path.insert(0, ROOT)
+    cache = {}
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            return
+        if msg[0] == 'prepare':
+            _, cfg, otype, n, warmup = msg
+            key = (cfg, otype, n)
+            if key not in cache:
+                cache.clear()
+                cache[key] = cpu_workload(cfg, otype, n, seed=1000 + cpu)
+            with np.errstate(all='ignore'):
+                for _ in range(warmup):
+                    cache[key]()
+            conn.send('ready')
+        else:
+            _, cfg, otype, n, steps = msg
+            step, times = cache[(cfg, otype, n)], []
+            with np.errstate(all='ignore'):
+                for _ in range(steps):
+                    t0 = time.perf_counter()
+                    step()
+                    times.append(time.perf_counter() - t0)
+            conn.send(times)
 
 
-def cpu_reference(steps, warmup, points_per_worker=1 << 22, max_workers=64):
-    """Reference algorithm on the host: numpy einsum is single-threaded, so one process per core, each with
-    its own slice (the same sharding the GPUs use). Returns (points/s, cores, sample description, ms/step)."""
-    import multiprocessing as mp
-    cores = max(1, min(os.cpu_count() or 1, max_workers))
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(points_per_worker, 1)) as pool:
-        for _ in range(warmup):
-            pool.map(_cpu_worker_step, range(cores))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            pool.map(_cpu_worker_step, range(cores))
-        dt = (time.perf_counter() - t0) / steps
-    total = points_per_worker * cores
-    return total / dt, cores, f'{cores} processes x 2^{int(np.log2(points_per_worker))} points per step (oracle port of the numpy backend, einsum optimize=True, order=F)', dt * 1e3
+class CpuFarm:
+    """One worker process per host core, each PINNED to its own CPU (numpy's einsum is single-threaded, so the batch
+    is sharded over processes exactly like it is over GPUs).  A measurement = every participating worker prepares
+    (builds inputs and integer tables, warm-up passes), then all start together and run `steps` passes; the
+    throughput of step s is sum over workers of items / time, and the MEDIAN over steps is reported."""
+
+    def __init__(self, max_workers=64):
+        import multiprocessing as mp
+        for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            os.environ[v] = '1'                      # one worker = one core, also inside BLAS-backed einsum paths
+        cpus = sorted(os.sched_getaffinity(0))[:max_workers]
+        ctx = mp.get_context('spawn')
+        self.workers = []
+        for cpu in cpus:
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_farm_worker, args=(child, cpu), daemon=True)
+            p.start()
+            self.workers.append((p, parent))
+        self.cores = len(cpus)
+
+    def measure(self, cfg, otype, n, workers, steps=3, warmup=1):
+        use = self.workers[:workers]
+        for _, c in use:
+            c.send(('prepare', cfg, otype, n, warmup))
+        for _, c in use:
+            assert c.recv() == 'ready'
+        for _, c in use:
+            c.send(('go', cfg, otype, n, steps))
+        times = np.array([c.recv() for _, c in use])          # [workers, steps]
+        per_step = (n / times).sum(axis=0)
+        return float(np.median(per_step)), float(np.median(times.max(axis=0)) * 1e3)
+
+    def baselines(self, cfg, unit):
+        """einsum + sparse operator, one core and all cores, for one configuration."""
+        out = {'unit': unit, 'kind': 'port', 'cores': self.cores,
+               'sample': {k: f'{v} items per worker per step' for k, v in CPU_SAMPLES[cfg].items()},
+               'how': 'oracle port of the reference numpy backend; workers pinned one per CPU; median over 3 steps after 1 warm-up'}
+        for otype in ('einsum', 'sparse'):
+            n = CPU_SAMPLES[cfg][otype]
+            out[f'{otype}_1core'], _ = self.measure(cfg, otype, n, 1)
+            out[f'{otype}_allcores'], _ = self.measure(cfg, otype, n, self.cores)
+        out['value'] = out['einsum_allcores']           # NumpyEinsumOperator is the reference's default otype
+        return out
+
+    def close(self):
+        for p, c in self.workers:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=5)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    value, cores, sample, ms = cpu_reference(max(1, args.steps), max(1, args.warmup))
+    farm = CpuFarm()
+    n = CPU_SAMPLES['cfg2']['einsum']
+    value, ms = farm.measure('cfg2', 'einsum', n, farm.cores, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    cores = farm.cores
+    farm.close()
+    sample = (f'{cores} pinned processes x 2^{int(np.log2(n))} points per step (oracle port of the numpy backend, '
+              'NumpyEinsumOperator: einsum optimize=True, order=F); median step')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
@@ -260,50 +373,253 @@ def time_steps(fn, steps, warmup, dist=None):
     return ms / steps
 
 
-def other_configs(torch, B200Context, rank, peak):
-    """The remaining BASELINE.json configurations on one GPU, device timed (supplementary)."""
+def rel_err(got, want):
+    """max over items of ||got - want||inf / ||want||inf (SURVEY.md 8d parity gate)."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.maximum(np.abs(want).max(axis=-1), 1e-300)
+    with np.errstate(all='ignore'):
+        e = np.abs(got - want).max(axis=-1) / scale
+    return float(np.nanmax(e)) if e.size else 0.0
+
+
+PARITY_N = 1 << 16
+# value gates of the benchmarked (fast) mode; derivation in profiles/r02_tolerances.md
+TOL = {'cfg1': 1e-5, 'cfg2': 1e-5, 'cfg4': 1e-5, 'cfg3_f32': 1e-3, 'cfg3_f64': 1e-10,
+       'cfg5_f32': (1e-5, 5e-3), 'cfg5_f64': (1e-12, 1e-10)}
+
+
+def entry(cfg, name, n, ms, bytes_per_item, peak, unit='products/s', **extra):
+    gbs = bytes_per_item * n / ms / 1e6
+    e = {'id': cfg, 'config': name, 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'unit': unit,
+         'roofline': {'bound': 'hbm', 'bytes_per_item': bytes_per_item, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                      'frac': gbs / peak}}
+    e.update(extra)
+    return e
+
+
+def run_cfg1(torch, B200Context, rank, peak, faithful=True):
+    """configs[0]: 3D PGA motor * motor, batch 2^20 (BASELINE size; 96 MB working set: L2-resident) and 2^26."""
+    from oracle import numga_oracle as O
     out = []
-
-    def entry(name, unit_bytes, n, ms, flops=None, note=None):
-        gbs = unit_bytes * n / ms / 1e6
-        e = {'config': name, 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': unit_bytes,
-             'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak}
-        if flops:
-            e['tflops'] = flops * n / ms / 1e9
-        if note:
-            e['note'] = note
-        out.append(e)
-
     pga = B200Context((3, 0, 1), dtype=torch.float32)
     S = pga.subspace
-    for n, tag in ((1 << 20, 'config 1: motor*motor, batch 2^20 (96 MB: L2-resident between launches)'),
-                   (1 << 26, 'config 1: motor*motor, batch 2^26')):
+    rng = np.random.default_rng(101)
+    ha, hb = rng.standard_normal((PARITY_N, 8)).astype(np.float32), rng.standard_normal((PARITY_N, 8)).astype(np.float32)
+    oc = O.context((3, 0, 1), np.float32)
+    want = (oc.multivector('even_grade', ha) * oc.multivector('even_grade', hb)).values
+    err = rel_err((pga.multivector.motor(ha) * pga.multivector.motor(hb)).numpy(), want)
+    for n in (1 << 20, 1 << 26):
         a, b = device_mv(pga, S.even_grade(), n, 11, rank), device_mv(pga, S.even_grade(), n, 12, rank)
-        ms = time_steps(lambda: a * b, 20, 3)
-        entry(tag, 96, n, ms, flops=88)
+        ms = time_steps(lambda: a * b, 50 if n == 1 << 20 else 20, 5)
+        extra = {}
         if n == 1 << 20:
-            # the eager call above is bound by the python/driver launch path (~35 us); 20 products recorded in one CUDA
-            # graph show the kernel itself
+            # host cost of one eager call (python dispatch + output allocation + C launch), GPU idle
+            torch.cuda.synchronize()
+            reps = 2000
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                a * b
+            host_us = (time.perf_counter() - t0) / reps * 1e6      # launches queue up: this is issue cost when < kernel time
+            torch.cuda.synchronize()
+
             def twenty(a, b):
                 for _ in range(20):
-                    out = a * b
-                return out
+                    o = a * b
+                return o
             g = pga.capture(twenty, a, b)
-            ms = time_steps(g.replay, 10, 3) / 20
-            entry('config 1: motor*motor, batch 2^20, 20 launches per CUDA graph replay (B200Context.capture)', 96, n, ms, flops=88)
+            ms_graph = time_steps(g.replay, 10, 3) / 20
+            extra = {'eager_call_us_wall': host_us, 'ms_in_cuda_graph': ms_graph,
+                     'frac_in_cuda_graph': 96 * n / ms_graph / 1e6 / peak,
+                     'l2_note': '96 MB working set fits the 126 MB L2: fractions above 1.0 of the HBM copy peak are L2 hits'}
+        if faithful:
+            fctx = B200Context((3, 0, 1), dtype=torch.float32, mode='faithful')
+            fa, fb = fctx.multivector(values=a.values, subspace=a.subspace), fctx.multivector(values=b.values, subspace=b.subspace)
+            extra['faithful_ms'] = time_steps(lambda: fa * fb, 20, 3)
+        out.append(entry('cfg1', f'config 1: 3D PGA motor*motor, fp32, batch 2^{int(np.log2(n))}, eager call', n, ms, 96, peak,
+                         flops_per_item=88, parity_ok=bool(err <= TOL['cfg1']), parity_err=err, parity_tol=TOL['cfg1'], **extra))
         del a, b
-    for dtype, tag, ub in ((torch.float32, 'fp32', 48), (torch.float64, 'fp64', 96)):
+    return out
+
+
+def run_cfg3(torch, B200Context, rank, peak, faithful=True):
+    """configs[2]: bivector -> exp -> normalized -> motor_log round trip, 2^28, fp32 and fp64, ONE kernel."""
+    from oracle import numga_oracle as O
+    out = []
+    issue = {}
+    ip = os.path.join(ROOT, 'profiles', 'r02_issue_slots.json')
+    if os.path.exists(ip):
+        issue = json.load(open(ip))
+    for dtype, tag, ub in ((torch.float32, 'f32', 48), (torch.float64, 'f64', 96)):
+        npd = np.float32 if tag == 'f32' else np.float64
         c = B200Context((3, 0, 1), dtype=dtype)
-        n = 1 << 28 if dtype == torch.float32 else 1 << 27
-        bv = device_mv(c, c.subspace.bivector(), n, 13, rank, scale=0.5)
         f = c.jit(lambda x: x.exp().normalized().motor_log())
-        ms = time_steps(lambda: f(bv), 5, 2)
+        hb = (0.5 * np.random.default_rng(103).standard_normal((PARITY_N, 6)))
+        with np.errstate(all='ignore'):
+            want64 = O.context((3, 0, 1), np.float64).multivector('bivector', hb).exp().normalized().motor_log().values
+            want = O.context((3, 0, 1), npd).multivector('bivector', hb.astype(npd)).exp().normalized().motor_log().values
+        got = f(c.multivector.bivector(hb.astype(npd))).numpy()
+        # the chain amplifies rounding: the gate is the reference's own error at this precision against the fp64 result
+        e_gpu, e_ref = rel_err(got, want64), rel_err(want, want64)
+        tol = TOL['cfg3_' + tag]
+        n = 1 << 28
+        bv = device_mv(c, c.subspace.bivector(), n, 13, rank, scale=0.5)
+        ms = time_steps(lambda: f(bv), 5, 3)
         prog = c.engine.cache[next(k for k in c.engine.cache if k[0][0] == 'jit')].program
-        entry(f'config 3: exp->normalized->motor_log fused round trip, {tag}, batch 2^{int(np.log2(n))}', ub, n, ms,
-              flops=prog.info['n_instr'], note='compute-bound: one kernel, all intermediates in registers; flops = live IR instructions')
+        extra = {}
+        if faithful and tag == 'f32':
+            fc = B200Context((3, 0, 1), dtype=dtype, mode='faithful')
+            ff = fc.jit(lambda x: x.exp().normalized().motor_log())
+            fb = fc.multivector(values=bv.values, subspace=bv.subspace)
+            extra['faithful_ms'] = time_steps(lambda: ff(fb), 3, 2)
+            extra['faithful_bit_exact_vs_oracle'] = bool(np.array_equal(ff(fc.multivector.bivector(hb.astype(npd))).numpy(), want))
+        e = entry('cfg3_' + tag, f'config 3: exp->normalized->motor_log round trip, {tag}, batch 2^28, one fused kernel', n, ms, ub, peak,
+                  flops_per_item=prog.info['n_instr'], tflops=prog.info['n_instr'] * n / ms / 1e9,
+                  parity_ok=bool(e_gpu <= max(tol, 2 * e_ref)), parity_err_vs_fp64=e_gpu, reference_err_vs_fp64=e_ref,
+                  parity_tol=tol, **extra)
+        e['roofline']['bound'] = 'fp32 issue' if tag == 'f32' else 'fp64 pipe'
+        e['roofline']['compute_bound'] = True
+        e['roofline']['issue_slot_utilisation_ncu'] = issue.get('cfg3_' + tag)
+        out.append(e)
         del bv
-    # exp alone: the generic bisection algorithm (the reference's default dispatch) vs the opt-in closed form
-    # (numga_b200.optimized, the counterpart of the reference's optional extension/optimized.py)
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_cfg4(torch, B200Context, rank, peak, faithful=True):
+    """configs[3]: CGA (4,1,0) full x full geometric product, 2^26, fp32, SIMT (tensor-core note in DESIGN.md)."""
+    from oracle import numga_oracle as O
+    cga = B200Context((4, 1, 0), dtype=torch.float32)
+    F = cga.subspace.full()
+    rng = np.random.default_rng(104)
+    hx, hy = rng.standard_normal((PARITY_N, 32)).astype(np.float32), rng.standard_normal((PARITY_N, 32)).astype(np.float32)
+    oc = O.context((4, 1, 0), np.float32)
+    want = (oc.multivector('multivector', hx) * oc.multivector('multivector', hy)).values
+    err = rel_err((cga.multivector(values=hx, subspace=F) * cga.multivector(values=hy, subspace=F)).numpy(), want)
+    n = 1 << 26
+    x, y = device_mv(cga, F, n, 14, rank), device_mv(cga, F, n, 15, rank)
+    ms = time_steps(lambda: x * y, 10, 3)
+    extra = {}
+    if faithful:
+        fc = B200Context((4, 1, 0), dtype=torch.float32, mode='faithful')
+        fx, fy = fc.multivector(values=x.values, subspace=F), fc.multivector(values=y.values, subspace=F)
+        extra['faithful_ms'] = time_steps(lambda: fx * fy, 5, 2)
+    e = entry('cfg4', 'config 4: CGA (4,1,0) full*full geometric product, fp32, batch 2^26 (SIMT, 1024 FMA/item)', n, ms, 384, peak,
+              flops_per_item=2016, tflops=2016 * n / ms / 1e9, parity_ok=bool(err <= TOL['cfg4']), parity_err=err,
+              parity_tol=TOL['cfg4'], **extra)
+    e['tensor_core_comparison'] = ('not run: every K[i,:,:] of the [32,32,32] table is a signed permutation, so a GEMM form computes '
+                                   '32x the flops (65.5 kflop/item => 1.1 PFLOP/s TF32 at the HBM rate, above the TF32 peak) and TF32 '
+                                   'misses the 1e-5 gate; see DESIGN.md "Tensor cores"')
+    del x, y
+    torch.cuda.empty_cache()
+    return [e]
+
+
+def physics_state(ctx, n_chains, rank, seed=16, host_rate=None):
+    from numga_b200.examples.physics import replicate_chains, setup_bodies
+    bodies, sets = setup_bodies(ctx, n_bodies=12)
+    big, bsets = replicate_chains(bodies, sets, n_chains)
+    if host_rate is not None:
+        big = big.copy(rate=big.rate + ctx.multivector.bivector(host_rate))
+    else:
+        big = big.copy(rate=big.rate + device_mv(ctx, ctx.subspace.bivector(), 12 * n_chains, seed, rank, scale=0.3))
+    return big, bsets
+
+
+def run_cfg5(torch, B200Context, rank, peak, n_target=1 << 24, unroll=10, faithful=True):
+    """configs[4]: rigid-body XPBD core step (numga/examples/physics/core.py Body.integrate, two colour sets) on ~2^24
+    bodies = independent 12-body chains.  Two kernels of the same physics are timed:
+      * `ChainStep`: ONE chain-resident kernel (state once through HBM per launch; `unroll` sub-steps per launch as the
+        reference's run_chain_numpy.py:26-30 drives it);
+      * `FusedStep`: six kernels per sub-step (round-1 arrangement), for comparison."""
+    from oracle import physics_oracle as P
+    from numga_b200 import runtime as rt
+    from numga_b200.examples import physics as X
+    out = []
+    for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+        npd = np.float32 if tag == 'f32' else np.float64
+        es = 4 if tag == 'f32' else 8
+        c = B200Context('x+y+z+w0', dtype=dtype)
+        # ---- parity of the timed kernels on 2^16 bodies against the oracle port of the reference's sub-step -------
+        pc = PARITY_N // 12
+        hrate = (0.3 * np.random.default_rng(105).standard_normal((12 * pc, 6))).astype(npd)
+        small, ssets = physics_state(c, pc, rank, host_rate=hrate)
+        arrays = physics_arrays(tag)
+        ob, osets = P.from_arrays(arrays, npd, n_chains=pc, rate=np.tile(arrays['init/rate'], (pc, 1)).astype(npd) + hrate)
+        with np.errstate(all='ignore'):
+            want1 = ob.integrate(PHYSICS_DT, osets)
+            want2 = want1.integrate(PHYSICS_DT, osets)
+        mt, rt_tol = TOL['cfg5_' + tag]
+        steppers = {'FusedStep': X.FusedStep(small, ssets)}
+        if hasattr(X, 'ChainStep'):
+            steppers['ChainStep'] = X.ChainStep(small, ssets, unroll=2)
+        parity = {}
+        for name, st in steppers.items():
+            if name == 'ChainStep':
+                got2 = st.integrate(small, PHYSICS_DT)
+            else:
+                got2 = st.integrate(st.integrate(small, PHYSICS_DT), PHYSICS_DT)
+            em, er = rel_err(got2.motor.numpy(), want2.motor.values), rel_err(got2.rate.numpy(), want2.rate.values)
+            parity[name] = {'motor_err': em, 'rate_err': er, 'ok': bool(em <= 2 * mt and er <= 2 * rt_tol), 'sub_steps': 2,
+                            'tol': [2 * mt, 2 * rt_tol]}
+        del small, ssets, steppers
+        # ---- timing ---------------------------------------------------------------------------------------------------
+        n_chains = n_target // 12
+        n_bodies = 12 * n_chains
+        big, bsets = physics_state(c, n_chains, rank)
+        n_constraints = sum(int(s.body_idx.shape[1]) for s in bsets)
+        state_once = (92 + 14) * es + (2 * 4 + 2 * 36 + 1) * es * n_constraints / n_bodies + 2 * 8 * n_constraints / n_bodies
+        fs = X.FusedStep(big, bsets)
+        state = [big]
+
+        def step():
+            state[0] = fs.integrate(state[0], PHYSICS_DT)
+        l0 = rt.launch_count()
+        step()
+        launches = rt.launch_count() - l0
+        ms6 = time_steps(step, 10, 3)
+        words = {}
+        for k, v in c.engine.cache.items():
+            if k[0][0] == 'jit':
+                live_in = sum(1 for op, a, b, _ in v.ir['instr'] if op == rt.OP_INPUT and v.program.in_mode[a] != rt.BROADCAST)
+                words[k[0][1].__name__] = live_in + sum(v.ir['out_width'])
+        split_bytes = ((words['pre'] + words['post']) * es * n_bodies +
+                       ((words['apply'] + words['v_apply']) * es + 2 * 2 * 8) * n_constraints) / n_bodies
+        e6 = entry('cfg5_' + tag, f'config 5: rigid-body XPBD sub-step, {tag}, {n_bodies} bodies in {n_chains} chains, FusedStep: '
+                   f'{launches} kernels per sub-step', n_bodies, ms6, state_once, peak, unit='body-steps/s',
+                   parity_ok=parity['FusedStep']['ok'], parity=parity['FusedStep'], kernel_launches_per_step=launches)
+        e6['roofline']['bytes_per_item_note'] = 'SURVEY.md 8d state-once algorithmic bytes (each state word once per sub-step)'
+        e6['roofline_multi_kernel_convention'] = {'bytes_per_item': split_bytes, 'achieved': split_bytes * n_bodies / ms6 / 1e6,
+                                                  'frac': split_bytes * n_bodies / ms6 / 1e6 / peak,
+                                                  'note': 'live inputs + outputs of the six kernels, incl. gathered inertia matrices'}
+        out.append(e6)
+        if hasattr(X, 'ChainStep'):
+            for u in (1, unroll):
+                cs = X.ChainStep(big, bsets, unroll=u)
+                state = [big]
+
+                def cstep():
+                    state[0] = cs.integrate(state[0], PHYSICS_DT)
+                l0 = rt.launch_count()
+                cstep()
+                launches = rt.launch_count() - l0
+                ms = time_steps(cstep, 5 if u > 1 else 10, 3)
+                e = entry('cfg5_' + tag, f'config 5: rigid-body XPBD, {tag}, {n_bodies} bodies, ChainStep: ONE chain-resident kernel, '
+                          f'{u} sub-step(s) per launch', n_bodies * u, ms, state_once / u, peak, unit='body-steps/s',
+                          parity_ok=parity['ChainStep']['ok'], parity=parity['ChainStep'], kernel_launches_per_step=launches,
+                          sub_steps_per_launch=u, bodies=n_bodies)
+                e['roofline']['bytes_per_item_note'] = ('state-once bytes per launch / sub-steps per launch: the state crosses HBM once '
+                                                        'per launch' + ('; compute-bound at this unroll' if u > 1 else ''))
+                e['finite'] = bool(torch.isfinite(state[0].motor.values).all().item() and torch.isfinite(state[0].rate.values).all().item())
+                out.append(e)
+                del cs
+        del big, bsets, fs, state
+        torch.cuda.empty_cache()
+    return out
+
+
+def extra_configs(torch, B200Context, rank, peak):
+    """--extra: supplementary measurements (not BASELINE configs)."""
+    out = []
     import numga_b200.optimized as opt
     c = B200Context((3, 0, 1), dtype=torch.float32)
     n = 1 << 28
@@ -312,67 +628,28 @@ def other_configs(torch, B200Context, rank, peak):
         (opt.enable if on else opt.disable)()
         f = c.jit(lambda x: x.exp())
         ms = time_steps(lambda: f(bv), 5, 2)
-        prog = c.engine.cache[next(k for k in c.engine.cache if k[0][0] == 'jit')].program
-        entry(f'config 3 part: bivector exp only, fp32, batch 2^28, {tag}', 56, n, ms, flops=prog.info['n_instr'])
+        out.append(entry('extra', f'bivector exp only, fp32, batch 2^28, {tag}', n, ms, 56, peak))
     opt.disable()
     del bv
-    cga = B200Context((4, 1, 0), dtype=torch.float32)
-    F = cga.subspace.full()
-    n = 1 << 26
-    x, y = device_mv(cga, F, n, 14, rank), device_mv(cga, F, n, 15, rank)
-    ms = time_steps(lambda: x * y, 10, 3)
-    entry('config 4: CGA (4,1,0) full*full geometric product, batch 2^26 (SIMT, 1024 FMA/item)', 384, n, ms, flops=2016)
-    # the tensor-core formulation of the same product, for the comparison BASELINE.json configs[3] asks for:
-    # materialise the outer product P[b, (i,j)] = a_i b_j and multiply by the [1024, 32] sign matrix with cuBLAS
-    # (TF32 tensor cores).  32x the flops of the sparse form and 4 KB of intermediate per item; library call, NOT the
-    # product path.
-    nb = 1 << 20
-    K = torch.zeros(1024, 32, device='cuda')
-    op = cga.algebra.operator.product(F, F)
-    idx = torch.as_tensor(op.index.astype(np.int64), device='cuda')
-    K[idx[:, 0] * 32 + idx[:, 1], idx[:, 2]] = torch.as_tensor(op.coeff.astype(np.float32), device='cuda')
-    xa, ya = x.values[:nb].contiguous(), y.values[:nb].contiguous()
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-
-    def tensor_core_form():
-        return (xa[:, :, None] * ya[:, None, :]).reshape(nb, 1024) @ K
-    ms_tc = time_steps(tensor_core_form, 5, 2)
-    ref = cga.multivector(values=xa, subspace=F) * cga.multivector(values=ya, subspace=F)
-    err_tc = float(((tensor_core_form() - ref.values).abs().amax(dim=-1) / ref.values.abs().amax(dim=-1)).max().item())
-    torch.backends.cuda.matmul.allow_tf32 = prev
-    e = {'config': 'config 4 comparison: tensor-core formulation (outer product + cuBLAS TF32 GEMM with the [1024,32] sign matrix), batch 2^20',
-         'items': nb, 'ms': ms_tc, 'items_per_s': nb / ms_tc * 1e3, 'bytes_per_item': 384, 'achieved_gbs': 384 * nb / ms_tc / 1e6,
-         'frac_of_hbm_peak': 384 * nb / ms_tc / 1e6 / peak, 'tflops': 2 * 1024 * 32 * nb / ms_tc / 1e9,
-         'max_rel_error_vs_simt': err_tc, 'simt_items_per_s': out[-1]['items_per_s'],
-         'note': 'every K[i,:,:] is a signed permutation: there is no contraction to amortise, so the GEMM form does 32x the flops '
-                 'and moves 4 KB/item of intermediate; TF32 also misses the 1e-5 parity gate. SIMT wins; tensor cores are not used.'}
-    out.append(e)
-    del x, y, xa, ya
-    for dtype, tag in ((torch.float32, 'fp32'), (torch.float64, 'fp64')):
-        out.append(physics_config(torch, B200Context, rank, peak, dtype, tag))
     out.append(training_step_config(torch, B200Context, rank, peak))
     out.extend(generic_physics_configs(torch, B200Context, rank, peak))
     return out
 
 
-def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22):
+def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22, modes=('eager', 'lazy')):
     """Supplementary: the rigid-body step written exactly like the reference (Body.integrate, one multivector method
     after the other), run eagerly (one kernel per method) and with automatic fusion (B200Context(lazy=True))."""
     from numga_b200 import runtime as rt
-    from numga_b200.examples.physics import replicate_chains, setup_bodies
     out = []
     n_chains = n_target // 12
-    for mode in ('eager', 'lazy'):
+    for mode in modes:
         ctx = B200Context('x+y+z+w0', dtype=torch.float32, lazy=(mode == 'lazy'))
-        bodies, sets = setup_bodies(ctx, n_bodies=12)
-        big, bsets = replicate_chains(bodies, sets, n_chains)
-        big = big.copy(rate=big.rate + device_mv(ctx, ctx.subspace.bivector(), 12 * n_chains, 16, rank, scale=0.3))
+        big, bsets = physics_state(ctx, n_chains, rank)
         big.rate.values
         state = [big]
 
         def step():
-            new = state[0].integrate(1 / 200, bsets)
+            new = state[0].integrate(PHYSICS_DT, bsets)
             new.motor.values, new.rate.values
             state[0] = new
         l0 = rt.launch_count()
@@ -380,9 +657,8 @@ def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22):
         launches = rt.launch_count() - l0
         ms = time_steps(step, 5, 2)
         n = 12 * n_chains
-        out.append({'config': f'supplementary: reference-style Body.integrate (unchanged formulas, {mode}: {launches} generated kernels per sub-step), fp32, {n} bodies',
-                    'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': 0, 'achieved_gbs': 0.0, 'frac_of_hbm_peak': 0.0,
-                    'kernel_launches_per_step': launches})
+        out.append({'id': 'extra', 'config': f'reference-style Body.integrate (unchanged formulas, {mode}: {launches} generated kernels per '
+                    f'sub-step), fp32, {n} bodies', 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'kernel_launches_per_step': launches})
         del big, bsets, state
         torch.cuda.empty_cache()
     return out
@@ -408,54 +684,26 @@ def training_step_config(torch, B200Context, rank, peak, n=1 << 26):
         loss.backward()
     ms = time_steps(step, 10, 3)
     nbytes = (16 + 16 + 4 + 4 + 16 + 16 + 4) * n          # fwd: x, y in, err out; torch sum; bwd: x, y, cotangent in
-    return {'config': f'supplementary: autograd training step (fit one motor to 2^{int(np.log2(n))} points: forward + torch sum + generated VJP kernel with in-kernel reduction)',
-            'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'bytes_per_item': nbytes / n, 'achieved_gbs': nbytes / ms / 1e6,
-            'frac_of_hbm_peak': nbytes / ms / 1e6 / peak, 'grad_finite': bool(torch.isfinite(b.grad).all().item())}
+    e = entry('extra', f'autograd training step (fit one motor to 2^{int(np.log2(n))} points: forward + torch sum + generated VJP '
+              'kernel with in-kernel reduction)', n, ms, nbytes / n, peak)
+    e['grad_finite'] = bool(torch.isfinite(b.grad).all().item())
+    return e
 
 
-def physics_config(torch, B200Context, rank, peak, dtype, tag, n_target=1 << 24):
-    """BASELINE.json configs[4]: the rigid-body core step (numga/examples/physics/core.py Body.integrate with two
-    constraint colour sets) on ~2^24 bodies = independent 12-body chains, as SIX fused kernels per sub-step."""
-    from numga_b200 import runtime as rt
-    from numga_b200.examples.physics import FusedStep, replicate_chains, setup_bodies
-    c = B200Context('x+y+z+w0', dtype=dtype)
-    bodies, sets = setup_bodies(c, n_bodies=12)
-    n_chains = n_target // 12
-    big, bsets = replicate_chains(bodies, sets, n_chains)
-    n_bodies = 12 * n_chains
-    n_constraints = sum(int(s.body_idx.shape[1]) for s in bsets)
-    big = big.copy(rate=big.rate + device_mv(c, c.subspace.bivector(), n_bodies, 16, rank, scale=0.3))
-    fs = FusedStep(big, bsets)
-    state = [big]
-
-    def step():
-        state[0] = fs.integrate(state[0], 1 / 200)
-    l0 = rt.launch_count()
-    step()
-    launches = rt.launch_count() - l0
-    ms = time_steps(step, 10, 3)
-    finite = bool(torch.isfinite(state[0].motor.values).all().item() and torch.isfinite(state[0].rate.values).all().item())
-    # compulsory traffic of the six-kernel split: live input components + outputs (+ gather indices) per item
-    es = 4 if dtype == torch.float32 else 8
-    words, instr = {}, {}
-    for k, v in c.engine.cache.items():
-        if k[0][0] != 'jit':
-            continue
-        name = k[0][1].__name__
-        live_in = sum(1 for op, a, b, _ in v.ir['instr'] if op == rt.OP_INPUT and v.program.in_mode[a] != rt.BROADCAST)
-        words[name] = live_in + sum(v.ir['out_width'])
-        instr[name] = v.program.info['n_instr']
-    per_body = (words['pre'] + words['post']) * es
-    per_constraint = (words['apply'] + words['v_apply']) * es + 2 * 2 * 8      # two int64 body indices, two kernels
-    total = per_body * n_bodies + per_constraint * n_constraints
-    flops = (instr['pre'] + instr['post']) * n_bodies + (instr['apply'] + instr['v_apply']) * n_constraints
-    gbs = total / ms / 1e6
-    return {'config': f'config 5: rigid-body XPBD sub-step (Body.integrate, 2 colour sets), {tag}, {n_bodies} bodies in {n_chains} chains, '
-                      f'{launches} fused kernels per sub-step', 'items': n_bodies, 'ms': ms, 'items_per_s': n_bodies / ms * 1e3,
-            'bytes_per_item': total / n_bodies, 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak,
-            'tflops': flops / ms / 1e9, 'kernel_launches_per_step': launches, 'state_finite': finite,
-            'note': 'bytes = live inputs + outputs of the six kernels (pre, apply x2, post, v_apply x2) incl. gathered inertia '
-                    'matrices; the state-once minimum of SURVEY.md 8d (728 B fp32) would need a single pass'}
+def host_roundtrip_control(rt, local, n_in_bytes, n_out_bytes, hin, hout, steps, dist):
+    """Raw-copy control of the host path: the same pinned buffers, the same chunking and streams as
+    ngb200_program_run_host, H2D of the inputs and D2H of the outputs, NO kernel; all ranks concurrently."""
+    import ctypes
+    if not hasattr(rt.lib, 'ngb200_host_copy_control'):
+        return None
+    fn = rt.lib.ngb200_host_copy_control
+    rt.check(fn(hin, n_in_bytes, hout, n_out_bytes, 0, 0, local))
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rt.check(fn(hin, n_in_bytes, hout, n_out_bytes, 0, 0, local))
+    return (time.perf_counter() - t0) / steps
 
 
 def run_ours(args):
@@ -517,6 +765,29 @@ def run_ours(args):
     value = world * n / ms * 1e3
     achieved = BYTES_PER_POINT * n / ms / 1e6
 
+    # ---- parity of the timed kernel on EVERY rank: first and last 2^16 points of this rank's slice against the oracle
+    # (the Philox stream is deterministic per offset = rank * n; the inputs are read back, the oracle runs on the host)
+    from oracle import numga_oracle as O
+    oc = O.context((3, 0, 1), np.float32)
+    out_dev = sandwich(R, p)
+    perr = 0.0
+    for sl in (slice(0, PARITY_N), slice(n - PARITY_N, n)):
+        hp = p.values[sl].cpu().numpy()
+        want = (oc.multivector('even_grade', R.numpy()) >> oc.multivector('antivector', hp)).values
+        perr = max(perr, rel_err(out_dev.values[sl].cpu().numpy(), want))
+    parity_ok = perr <= TOL['cfg2']
+    if dist is not None:
+        t = torch.tensor([0.0 if parity_ok else 1.0, perr], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity_ok_all, perr_all = bool(t[0].item() == 0.0), float(t[1].item())
+    else:
+        parity_ok_all, perr_all = bool(parity_ok), perr
+    fctx = B200Context((3, 0, 1), dtype=torch.float32, device=f'cuda:{local}', mode='faithful')
+    fsand = fctx.jit(lambda r, x: r >> x)
+    fR, fp = fctx.multivector(values=R.values, subspace=R.subspace), fctx.multivector(values=p.values, subspace=p.subspace)
+    faithful_ms = time_steps(lambda: fsand(fR, fp), 5, 2)
+    del out_dev
+
     # ---- end to end through the C-ABI host-buffer call ---------------------------------------------------------
     import ctypes
     all_cpus = os.sched_getaffinity(0)
@@ -550,16 +821,23 @@ def run_ours(args):
     for _ in range(e2e_steps):
         prog.run_host(ins, outs, e2e_n, device=local)           # synchronous: returns when outputs are on the host
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
     check = sandwich(R, p).values[:1 << 16].T.cpu().numpy()
     e2e_ok = bool(np.array_equal(check, host_q[:, :1 << 16]))
+    ctrl_s = host_roundtrip_control(rt, local, 16 * e2e_n, 16 * e2e_n, hin, hout, e2e_steps, dist)   # (overwrites host_q)
+    if dist is not None:
+        t = torch.tensor([e2e_s, ctrl_s or 0.0], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s, ctrl_s = float(t[0].item()), (float(t[1].item()) if ctrl_s else None)
     e2e = {'value': world * e2e_n / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': 16 * e2e_n + 32,
            'd2h_bytes_per_step': 16 * e2e_n, 'steps': e2e_steps, 'points_per_gpu': e2e_n,
            'matches_device_result': e2e_ok, 'numa_local_cpus': numa,
            'path': 'ngb200_program_run_host (pinned host SoA buffers, 128 MB chunks, H2D/kernel/D2H pipelined over 4 streams)'}
+    if ctrl_s:
+        e2e['host_ceiling_points_s'] = world * e2e_n / ctrl_s
+        e2e['frac_of_host_ceiling'] = ctrl_s / e2e_s
+        e2e['host_ceiling_how'] = ('ngb200_host_copy_control: same pinned buffers, chunks and streams, H2D of the inputs + D2H of the '
+                                   'outputs, no kernel, all ranks concurrently; pinned GB/s per GPU = '
+                                   f'{32 * e2e_n / ctrl_s / 1e9:.1f}')
     for h in (hin, hout, hR):
         rt.lib.ngb200_host_free(h)
     os.sched_setaffinity(0, all_cpus)        # the CPU baseline below gets every host core back
@@ -573,13 +851,38 @@ def run_ours(args):
         g_ms = time_steps(lambda: dist.all_gather_into_tensor(dst, src), 5, 2, dist)
         gather = {'bytes_per_rank': src.numel() * 4, 'ms': g_ms, 'algbw_gbs': src.numel() * 4 * (world - 1) / g_ms / 1e6,
                   'note': 'NCCL all_gather of a 2^24-point output slice per rank; results stay sharded by default'}
+        del src, dst
+    del p
+    torch.cuda.empty_cache()
+
+    # ---- multi-GPU: the physics configuration sharded by chain (no exchange), every rank its own chains ------------
+    physics_multi = None
+    if dist is not None and not args.no_configs:
+        from numga_b200.examples import physics as X
+        c5 = B200Context('x+y+z+w0', dtype=torch.float32, device=f'cuda:{local}')
+        big, bsets = physics_state(c5, (1 << 24) // 12, rank)
+        stepper = X.ChainStep(big, bsets, unroll=1) if hasattr(X, 'ChainStep') else X.FusedStep(big, bsets)
+        st = [big]
+
+        def pstep():
+            st[0] = stepper.integrate(st[0], PHYSICS_DT)
+        ms5 = time_steps(pstep, 10, 3, dist)
+        nb = 12 * ((1 << 24) // 12)
+        physics_multi = {'config': 'config 5 sharded by chain, fp32, 2^24 bodies per GPU, ' + type(stepper).__name__,
+                         'body_steps_per_s': world * nb / ms5 * 1e3, 'ms': ms5, 'bodies_per_gpu': nb}
+        del big, bsets, st, stepper
+        torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'r01_sandwich_traffic.json')
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, 'profiles', 'r02_sandwich_traffic.json')
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, 'profiles', 'r01_sandwich_traffic.json')
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get('dram_bytes_per_launch'), {'file': os.path.relpath(tp, ROOT), 'commit': tj.get('commit'),
+                                                                      'kernel_source_hash': tj.get('kernel_source_hash')}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -589,16 +892,43 @@ def run_ours(args):
                        'l2': f'inputs+outputs {2 * 16 * n / 1e9:.1f} GB per GPU per step >> 126 MB L2 (no flush needed)'},
             'clocks': clock_summary, 'gpu_launches': launches, 'e2e': e2e,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': BYTES_PER_POINT * n, 'kernel_ms': ms},
+                         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': BYTES_PER_POINT * n, 'kernel_ms': ms,
+                         'kernel_source_hash': getattr(prog, 'source_hash', None)},
+            'parity_ok_all_ranks': parity_ok_all, 'parity_err_max_over_ranks': perr_all, 'parity_tol': TOL['cfg2'],
+            'parity_how': 'every rank: first and last 2^16 points of its slice, timed kernel vs oracle port on the host',
+            'faithful_ms_per_step': faithful_ms,
         }
         if gather:
             line['gather'] = gather
-    if args.configs and world == 1:
-        line['configs'] = other_configs(torch, B200Context, rank, peak)
+        if physics_multi:
+            line['physics_sharded'] = physics_multi
+    if world == 1 and not args.no_configs:
+        cfgs = []
+        cfgs += run_cfg1(torch, B200Context, rank, peak)
+        cfgs.append(entry('cfg2', 'config 2 (headline, see top level): R >> p, 2^28 points, broadcast motor, fp32', n, ms, 32, peak,
+                          unit='points/s', flops_per_item=28, parity_ok=parity_ok_all, parity_err=perr_all, parity_tol=TOL['cfg2'],
+                          faithful_ms=faithful_ms))
+        cfgs += run_cfg3(torch, B200Context, rank, peak)
+        cfgs += run_cfg4(torch, B200Context, rank, peak)
+        cfgs += run_cfg5(torch, B200Context, rank, peak)
+        if args.extra:
+            cfgs += extra_configs(torch, B200Context, rank, peak)
+        line['configs'] = cfgs
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample, _ = cpu_reference(3, 1)
-        line['cpu_baseline'] = {'value': v, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        farm = CpuFarm()
+        units = {'cfg1': 'products/s', 'cfg2': 'points/s', 'cfg3_f32': 'products/s', 'cfg3_f64': 'products/s', 'cfg4': 'products/s',
+                 'cfg5_f32': 'body-steps/s', 'cfg5_f64': 'body-steps/s'}
+        wanted = list(units) if not args.no_configs else ['cfg2']
+        base = {cfg: farm.baselines(cfg, units[cfg]) for cfg in wanted}
+        farm.close()
+        b2 = base['cfg2']
+        line['cpu_baseline'] = {'value': b2['einsum_allcores'], 'unit': 'points/s', 'cores': b2['cores'], 'kind': 'port',
+                                'sample': f"{b2['cores']} pinned processes x 2^22 points per step (NumpyEinsumOperator port), median step",
+                                'einsum_1core': b2['einsum_1core'], 'sparse_1core': b2['sparse_1core'], 'sparse_allcores': b2['sparse_allcores']}
+        for e in line.get('configs', []):
+            if e['id'] in base:
+                e['cpu_baseline'] = base[e['id']]
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -613,8 +943,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--points', type=int, default=POINTS_PER_GPU, help='points per GPU (default 2^28, the BASELINE.json size)')
-    ap.add_argument('--configs', action='store_true', help='also time the other BASELINE.json configurations (1 GPU)')
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-configs', action='store_true', help='headline configuration only (skip BASELINE configs 1, 3, 4, 5)')
+    ap.add_argument('--configs', action='store_true', help='(default now) kept for compatibility')
+    ap.add_argument('--extra', action='store_true', help='also run the supplementary measurements')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

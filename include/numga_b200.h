@@ -174,6 +174,25 @@ int ngb200_program_launch(ngb200_program *prog, const ngb200_operand *inputs, co
 int ngb200_program_run_host(ngb200_program *prog, const ngb200_operand *inputs, const ngb200_operand *outputs,
                             const double *params, int64_t batch, int32_t device, int64_t chunk_items);
 
+/* Raw-copy control for benchmarks: the chunked multi-stream H2D of in_bytes + D2H of out_bytes that
+ * ngb200_program_run_host performs, with no kernel (chunk_bytes / streams 0 = the pipeline's defaults).
+ * host_out receives unspecified data. */
+int ngb200_host_copy_control(void *host_in, int64_t in_bytes, void *host_out, int64_t out_bytes, int64_t chunk_bytes,
+                             int32_t streams, int32_t device);
+
+/* Launch plans: the steady state of an eager backend (same program, same operand layout, fresh pointers every
+ * call; XOperator.__call__ allocates its result each time, numga/backend/numpy/operator.py:40-49,117-132).
+ * A plan freezes kernel choice, grid sizes and the parameter block for one layout + batch on the CURRENT device;
+ * ngb200_plan_launch patches pointers and issues the kernel(s): no validation loops, no allocation.
+ * Layouts are given as operands whose `ptr` is ignored; programs with INDEXED / TILED / REDUCED operands are not
+ * plannable (NGB200_ERR_INVALID).  A plan must not outlive its program. */
+typedef struct ngb200_plan ngb200_plan;
+int ngb200_plan_create(ngb200_program *prog, const ngb200_operand *input_layout, const ngb200_operand *output_layout,
+                       int64_t batch, ngb200_plan **out);
+int ngb200_plan_launch(ngb200_plan *plan, void *const *input_ptrs, void *const *output_ptrs, const double *params,
+                       void *stream);
+void ngb200_plan_destroy(ngb200_plan *plan);
+
 int ngb200_host_alloc(void **ptr, int64_t bytes);
 int ngb200_host_free(void *ptr);
 

@@ -66,7 +66,7 @@ extern "C" int64_t ngb200_launch_count(void) { return g_launches.load(); }
 #define NGB_STR(x) NGB_STR2(x)
 #define DRV_FUNCS(X)                                                                              \
     X(cuInit) X(cuGetErrorString) X(cuCtxGetCurrent) X(cuCtxSetCurrent) X(cuCtxGetDevice)         \
-    X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData)        \
+    X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData) X(cuModuleUnload) \
     X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute) X(cuFuncSetAttribute)                                \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemAlloc) X(cuMemFree)                     \
     X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuStreamCreate)                \
@@ -828,7 +828,12 @@ static std::string default_cache_dir() {
         size_t k = p.rfind('/');
         if (k != std::string::npos) return p.substr(0, k) + "/_kcache";
     }
-    return "/tmp/numga_b200_kcache";
+    // last resort (library path unknown): a per-user directory, never a shared predictable path in /tmp
+    const char *xdg = getenv("XDG_CACHE_HOME");
+    const char *home = getenv("HOME");
+    std::string base = (xdg && *xdg) ? std::string(xdg) : (home && *home) ? std::string(home) + "/.cache" : std::string("/tmp/.cache-") + std::to_string((long)getuid());
+    mkdir(base.c_str(), 0700);
+    return base + "/numga_b200_kcache";
 }
 
 extern "C" int ngb200_set_cache_dir(const char *path) {
@@ -839,7 +844,7 @@ extern "C" int ngb200_set_cache_dir(const char *path) {
 
 static std::string cache_dir() {
     if (g_cache_dir.empty()) g_cache_dir = default_cache_dir();
-    mkdir(g_cache_dir.c_str(), 0755);
+    mkdir(g_cache_dir.c_str(), 0700);
     return g_cache_dir;
 }
 
@@ -1198,6 +1203,22 @@ extern "C" int ngb200_operator_create(const int32_t *terms, int32_t n_terms, int
 extern "C" void ngb200_program_destroy(ngb200_program *P) {
     if (!P) return;
     host_pipe_destroy(P->host);
+    if (g_drv.ok) {
+        // unload the device code of every device this program ran on (transient programs -- one per operator mask,
+        // lazy DAG structure or VJP variant -- would otherwise leak module memory for the life of the process)
+        for (int d = 0; d < kMaxDevices; ++d) {
+            Loaded &L = P->loaded[d];
+            if (!L.ready.load() || !L.mod) continue;
+            CUcontext prev = nullptr, ctx = nullptr;
+            CUdevice dev;
+            if (g_drv.p_cuCtxGetCurrent(&prev) != CUDA_SUCCESS) continue;
+            if (g_drv.p_cuDeviceGet(&dev, d) != CUDA_SUCCESS || g_drv.p_cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS) continue;
+            g_drv.p_cuCtxSetCurrent(ctx);
+            g_drv.p_cuModuleUnload(L.mod);
+            g_drv.p_cuCtxSetCurrent(prev);
+            L.mod = nullptr;
+        }
+    }
     delete P;
 }
 
@@ -1267,10 +1288,11 @@ static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t wor
     if (tpb <= 0) tpb = P->tpb;
     const size_t nin = P->in_width.size(), nout = P->out_width.size();
     const size_t nin_s = nin ? nin : 1, nout_s = nout ? nout : 1, np_s = P->n_params > 0 ? P->n_params : 1;
-    std::vector<char> buf(P->param_bytes, 0);
+    alignas(16) char buf[4096];                        // param_bytes <= 4000 is checked at creation: no heap allocation per launch
+    memset(buf, 0, P->param_bytes);
     const size_t ob = P->any_tiled ? 48 : 32;          // bytes per operand in the kernel's Params
     const int es = esize(P->dtype);
-    auto put = [&](size_t slot, const DevOperand &d) { memcpy(buf.data() + slot * ob, &d, ob); };
+    auto put = [&](size_t slot, const DevOperand &d) { memcpy(buf + slot * ob, &d, ob); };
     for (size_t k = 0; k < nin; ++k) {
         bool moves = P->in_mode[k] == NGB200_VARYING;
         put(k, {(char *)in[k].ptr + (moves ? offset * in[k].batch_stride * es : 0), in[k].comp_stride,
@@ -1284,13 +1306,13 @@ static int launch_one(ngb200_program *P, CUfunction f, int grid_cap, int64_t wor
                         out[k].batch_stride,
                         P->out_mode[k] == NGB200_INDEXED ? (const long long *)out[k].index + offset : nullptr, 0, 0});
     }
-    double *sc = reinterpret_cast<double *>(buf.data() + ob * (nin_s + nout_s));
+    double *sc = reinterpret_cast<double *>(buf + ob * (nin_s + nout_s));
     for (int k = 0; k < P->n_params; ++k) sc[k] = params ? params[k] : 0.0;
-    *reinterpret_cast<long long *>(buf.data() + ob * (nin_s + nout_s) + 8 * np_s) = n;
+    *reinterpret_cast<long long *>(buf + ob * (nin_s + nout_s) + 8 * np_s) = n;
     int64_t blocks = (work + tpb - 1) / tpb;
     if (blocks > grid_cap) blocks = grid_cap;
     if (blocks < 1) blocks = 1;
-    void *args[] = {buf.data()};
+    void *args[] = {buf};
     CU(cuLaunchKernel(f, (unsigned)blocks, 1, 1, (unsigned)tpb, 1, 1, (unsigned)smem, stream, args, nullptr));
     g_launches.fetch_add(1);
     return NGB200_OK;
@@ -1371,6 +1393,160 @@ extern "C" int ngb200_program_launch(ngb200_program *P, const ngb200_operand *in
 }
 
 // ------------------------------------------------------------------------------------------
+// launch plans: everything about a launch that does not change between calls, decided once
+// ------------------------------------------------------------------------------------------
+// The eager path of a backend issues the same program on operands of the same layout over and over with fresh
+// pointers (every operator call allocates its result).  A plan freezes kernel choice, grid sizes and the parameter
+// block for one (layout, batch, device); launching it is: patch the pointers into a stack copy of the block,
+// re-check pointer alignment for the vector kernel, cuLaunchKernel.  No validation loops, no heap allocation, no
+// driver queries.
+struct ngb200_plan {
+    ngb200_program *P = nullptr;
+    int device = 0;
+    int n_in = 0, n_out = 0, n_params = 0;
+    size_t ob = 32, param_bytes = 0, scal_off = 0;
+    bool vec_possible = false;
+    int64_t batch = 0;
+    struct Shot {
+        CUfunction f = nullptr;
+        unsigned blocks = 0, tpb = 0;
+        int64_t offset = 0;                 // first item of this shot
+        char block[1024];                   // parameter block with null pointers
+    };
+    Shot vec_main, vec_tail, scalar;        // vec path = main (+ tail when batch % vec); scalar path = one shot
+    bool has_tail = false;
+    std::vector<int64_t> in_bs, out_bs;     // batch strides in elements (to offset tail pointers)
+    std::vector<int> in_moves, out_moves;
+};
+
+static void plan_fill(ngb200_plan *pl, ngb200_plan::Shot &shot, CUfunction f, int grid_cap, int64_t work, int64_t n,
+                      int64_t offset, const ngb200_operand *in, const ngb200_operand *out, int tpb) {
+    ngb200_program *P = pl->P;
+    memset(shot.block, 0, sizeof shot.block);
+    const size_t nin_s = pl->n_in ? pl->n_in : 1, nout_s = pl->n_out ? pl->n_out : 1, np_s = P->n_params > 0 ? P->n_params : 1;
+    for (int k = 0; k < pl->n_in; ++k) {
+        DevOperand d{nullptr, in[k].comp_stride, P->in_mode[k] == NGB200_BROADCAST ? 0 : in[k].batch_stride, nullptr, 0, 0};
+        memcpy(shot.block + k * pl->ob, &d, pl->ob);
+    }
+    for (int k = 0; k < pl->n_out; ++k) {
+        DevOperand d{nullptr, out[k].comp_stride, out[k].batch_stride, nullptr, 0, 0};
+        memcpy(shot.block + (nin_s + k) * pl->ob, &d, pl->ob);
+    }
+    *reinterpret_cast<long long *>(shot.block + pl->ob * (nin_s + nout_s) + 8 * np_s) = n;
+    int64_t blocks = (work + tpb - 1) / tpb;
+    if (blocks > grid_cap) blocks = grid_cap;
+    if (blocks < 1) blocks = 1;
+    shot.f = f;
+    shot.blocks = (unsigned)blocks;
+    shot.tpb = (unsigned)tpb;
+    shot.offset = offset;
+}
+
+extern "C" int ngb200_plan_create(ngb200_program *P, const ngb200_operand *in, const ngb200_operand *out, int64_t batch,
+                                  ngb200_plan **result) {
+    if (!P || !out || !result || (!in && !P->in_width.empty())) return fail(NGB200_ERR_INVALID, "null argument");
+    if (batch <= 0) return fail(NGB200_ERR_INVALID, "plans need a positive batch");
+    if (P->any_indexed || P->any_reduced || P->any_tiled || P->stage_tpb > 0)
+        return fail(NGB200_ERR_INVALID, "plans cover VARYING / BROADCAST operands only (use ngb200_program_launch)");
+    if (P->param_bytes > sizeof(ngb200_plan::Shot::block)) return fail(NGB200_ERR_INVALID, "too many operands for a plan");
+    int rc = need_driver();
+    if (rc) return rc;
+    int dev = 0;
+    rc = current_device(&dev, -1);
+    if (rc) return rc;
+    Loaded *L = nullptr;
+    rc = load_on_device(P, dev, &L);
+    if (rc) return rc;
+    ngb200_plan *pl = new ngb200_plan;
+    pl->P = P;
+    pl->device = dev;
+    pl->n_in = (int)P->in_width.size();
+    pl->n_out = (int)P->out_width.size();
+    pl->n_params = P->n_params;
+    pl->ob = 32;
+    pl->param_bytes = P->param_bytes;
+    pl->scal_off = pl->ob * ((pl->n_in ? pl->n_in : 1) + (pl->n_out ? pl->n_out : 1));
+    pl->batch = batch;
+    const int es = esize(P->dtype);
+    for (int k = 0; k < pl->n_in; ++k) { pl->in_bs.push_back(in[k].batch_stride); pl->in_moves.push_back(P->in_mode[k] == NGB200_VARYING); }
+    for (int k = 0; k < pl->n_out; ++k) { pl->out_bs.push_back(out[k].batch_stride); pl->out_moves.push_back(1); }
+    bool vec_ok = P->has_vec && batch >= P->vec;
+    if (vec_ok) {
+        auto strides_ok = [&](const ngb200_operand &o, int width) {
+            if (width == 0) return true;
+            if (P->vec == 1) return o.batch_stride == 1;
+            return o.batch_stride == 1 && (width == 1 || (o.comp_stride * es) % 16 == 0);
+        };
+        for (int k = 0; k < pl->n_in && vec_ok; ++k)
+            if (P->in_mode[k] == NGB200_VARYING) vec_ok = strides_ok(in[k], P->in_width[k]);
+        for (int k = 0; k < pl->n_out && vec_ok; ++k) vec_ok = strides_ok(out[k], P->out_width[k]);
+    }
+    pl->vec_possible = vec_ok;
+    if (vec_ok) {
+        const int64_t nvec = batch / P->vec, done = nvec * P->vec;
+        plan_fill(pl, pl->vec_main, L->fvec, L->grid_vec, nvec, done, 0, in, out, P->tpb);
+        pl->has_tail = done < batch;
+        if (pl->has_tail) plan_fill(pl, pl->vec_tail, L->fscalar, L->grid_scalar, batch - done, batch - done, done, in, out, P->tpb);
+    }
+    CUfunction fs = L->fscalar;
+    if (L->fscalar_u) {
+        bool unit = true;
+        for (int k = 0; k < pl->n_in && unit; ++k)
+            if (P->in_width[k] > 0 && P->in_mode[k] == NGB200_VARYING) unit = in[k].batch_stride == 1;
+        for (int k = 0; k < pl->n_out && unit; ++k)
+            if (P->out_width[k] > 0) unit = out[k].batch_stride == 1;
+        if (unit) fs = L->fscalar_u;
+    }
+    plan_fill(pl, pl->scalar, fs, L->grid_scalar, batch, batch, 0, in, out, P->tpb);
+    *result = pl;
+    return NGB200_OK;
+}
+
+extern "C" void ngb200_plan_destroy(ngb200_plan *pl) { delete pl; }
+
+static inline int plan_shoot(ngb200_plan *pl, const ngb200_plan::Shot &shot, void *const *in_ptrs, void *const *out_ptrs,
+                             const double *params, CUstream stream) {
+    alignas(16) char buf[sizeof shot.block];
+    memcpy(buf, shot.block, pl->param_bytes);
+    const int es = esize(pl->P->dtype);
+    const size_t nin_s = pl->n_in ? pl->n_in : 1;
+    for (int k = 0; k < pl->n_in; ++k) {
+        char *p = (char *)in_ptrs[k] + (pl->in_moves[k] ? shot.offset * pl->in_bs[k] * es : 0);
+        memcpy(buf + k * pl->ob, &p, sizeof p);
+    }
+    for (int k = 0; k < pl->n_out; ++k) {
+        char *p = (char *)out_ptrs[k] + shot.offset * pl->out_bs[k] * es;
+        memcpy(buf + (nin_s + k) * pl->ob, &p, sizeof p);
+    }
+    if (pl->n_params) memcpy(buf + pl->scal_off, params, 8 * (size_t)pl->n_params);
+    void *args[] = {buf};
+    CU(cuLaunchKernel(shot.f, shot.blocks, 1, 1, shot.tpb, 1, 1, 0, stream, args, nullptr));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return NGB200_OK;
+}
+
+// The calling thread's current CUDA context must be the one the plan was created in (true whenever `stream` is the
+// caller's current stream on that device).
+extern "C" int ngb200_plan_launch(ngb200_plan *pl, void *const *in_ptrs, void *const *out_ptrs, const double *params,
+                                  void *stream) {
+    if (!pl) return fail(NGB200_ERR_INVALID, "null plan");
+    bool vec = pl->vec_possible;
+    if (vec && pl->P->vec > 1) {
+        for (int k = 0; k < pl->n_in && vec; ++k)
+            if (pl->in_moves[k] && pl->P->in_width[k]) vec = ((uintptr_t)in_ptrs[k] & 15) == 0;
+        for (int k = 0; k < pl->n_out && vec; ++k)
+            if (pl->P->out_width[k]) vec = ((uintptr_t)out_ptrs[k] & 15) == 0;
+    }
+    CUstream s = (CUstream)stream;
+    if (vec) {
+        int rc = plan_shoot(pl, pl->vec_main, in_ptrs, out_ptrs, params, s);
+        if (rc || !pl->has_tail) return rc;
+        return plan_shoot(pl, pl->vec_tail, in_ptrs, out_ptrs, params, s);
+    }
+    return plan_shoot(pl, pl->scalar, in_ptrs, out_ptrs, params, s);
+}
+
+// ------------------------------------------------------------------------------------------
 // host-buffer execution: chunked H2D -> kernel -> D2H over several streams
 // ------------------------------------------------------------------------------------------
 extern "C" int ngb200_host_alloc(void **ptr, int64_t bytes) {
@@ -1445,10 +1621,46 @@ static int copy_chunk(bool to_device, const ngb200_operand &h, int width, int es
     return fail(NGB200_ERR_INVALID, "host operand must be SoA (batch_stride 1) or packed AoS (comp_stride 1, batch_stride width)");
 }
 
+// (re)build the staging resources for one configuration; on ANY failure everything allocated so far is released
+// and the pipe is left empty, so a later call starts from scratch instead of running on null buffers
+static int host_pipe_configure(ngb200_program *P, HostPipe &run, int dev, int64_t chunk_items, int n_slots) {
+    if (run.device == dev && run.chunk_items == chunk_items && (int)run.slots.size() == n_slots) return NGB200_OK;
+    run.release();
+    const int es = esize(P->dtype);
+    const size_t nin = P->in_width.size(), nout = P->out_width.size();
+    HostPipe fresh;
+    fresh.slots.resize(n_slots);
+    fresh.bcast.assign(nin, 0);
+    auto build = [&]() -> int {
+        for (HostPipe::Slot &s : fresh.slots) {
+            s.in.assign(nin, 0);
+            s.out.assign(nout, 0);
+            CU(cuStreamCreate(&s.stream, CU_STREAM_NON_BLOCKING));
+            for (size_t k = 0; k < nin; ++k)
+                if (P->in_mode[k] == NGB200_VARYING && P->in_width[k]) CU(cuMemAlloc(&s.in[k], (size_t)chunk_items * P->in_width[k] * es));
+            for (size_t k = 0; k < nout; ++k)
+                if (P->out_width[k]) CU(cuMemAlloc(&s.out[k], (size_t)chunk_items * P->out_width[k] * es));
+        }
+        for (size_t k = 0; k < nin; ++k)
+            if (P->in_mode[k] == NGB200_BROADCAST && P->in_width[k]) CU(cuMemAlloc(&fresh.bcast[k], (size_t)P->in_width[k] * es));
+        return NGB200_OK;
+    };
+    int rc = build();
+    if (rc) { fresh.release(); return rc; }
+    fresh.device = dev;
+    fresh.chunk_items = chunk_items;
+    run = fresh;                      // plain handles: the pipe owns them from here on
+    fresh.slots.clear();
+    fresh.bcast.clear();
+    return NGB200_OK;
+}
+
 extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *in, const ngb200_operand *out,
                                        const double *params, int64_t batch, int32_t device, int64_t chunk_items) {
-    if (!P || !out) return fail(NGB200_ERR_INVALID, "null argument");
-    if (P->any_indexed) return fail(NGB200_ERR_INVALID, "run_host does not support indexed operands");
+    if (!P || !out || (!in && !P->in_width.empty())) return fail(NGB200_ERR_INVALID, "null argument");
+    if (P->any_indexed) return fail(NGB200_ERR_INVALID, "run_host does not support indexed / tiled operands");
+    if (P->any_reduced) return fail(NGB200_ERR_INVALID, "run_host does not support NGB200_REDUCED outputs (batch sums need one device accumulator across chunks)");
+    if (P->n_params > 0 && !params) return fail(NGB200_ERR_INVALID, "program needs %d scalar params", P->n_params);
     int rc = need_driver();
     if (rc) return rc;
     int dev;
@@ -1468,57 +1680,115 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
     std::lock_guard<std::mutex> pipe_lock(P->host_mu);      // one host run per program at a time (shared staging)
     if (!P->host) P->host = new HostPipe;
     HostPipe &run = *P->host;
-    if (run.device != dev || run.chunk_items != chunk_items || (int)run.slots.size() != n_slots) {
-        run.release();
-        run.device = dev;
-        run.chunk_items = chunk_items;
-        run.slots.resize(n_slots);
-        run.bcast.assign(nin, 0);
-        for (HostPipe::Slot &s : run.slots) {
-            CU(cuStreamCreate(&s.stream, CU_STREAM_NON_BLOCKING));
-            s.in.assign(nin, 0);
-            s.out.assign(nout, 0);
-            for (size_t k = 0; k < nin; ++k)
-                if (P->in_mode[k] == NGB200_VARYING && P->in_width[k]) CU(cuMemAlloc(&s.in[k], (size_t)chunk_items * P->in_width[k] * es));
-            for (size_t k = 0; k < nout; ++k)
-                if (P->out_width[k]) CU(cuMemAlloc(&s.out[k], (size_t)chunk_items * P->out_width[k] * es));
-        }
-        for (size_t k = 0; k < nin; ++k)
-            if (P->in_mode[k] == NGB200_BROADCAST && P->in_width[k]) CU(cuMemAlloc(&run.bcast[k], (size_t)P->in_width[k] * es));
-    }
-    // broadcast operands: one small upload, visible to all streams after a sync
-    for (size_t k = 0; k < nin; ++k) {
-        if (P->in_mode[k] != NGB200_BROADCAST || !P->in_width[k]) continue;
-        std::vector<char> packed((size_t)P->in_width[k] * es);
-        for (int c = 0; c < P->in_width[k]; ++c) memcpy(&packed[(size_t)c * es], (char *)in[k].ptr + (size_t)c * in[k].comp_stride * es, es);
-        CU(cuMemcpyHtoDAsync(run.bcast[k], packed.data(), packed.size(), run.slots[0].stream));
-        CU(cuStreamSynchronize(run.slots[0].stream));
-    }
-    std::vector<ngb200_operand> din(nin ? nin : 1), dout(nout);
-    int64_t chunk_index = 0;
-    for (int64_t first = 0; first < batch; first += chunk_items, ++chunk_index) {
-        HostPipe::Slot &s = run.slots[chunk_index % n_slots];
-        int64_t items = std::min(chunk_items, batch - first);
+    rc = host_pipe_configure(P, run, dev, chunk_items, n_slots);
+    if (rc) return rc;
+    // From here on copies are in flight on the caller's host buffers: every exit path drains all slot streams first.
+    auto body = [&]() -> int {
+        // broadcast operands: one small upload, visible to all streams after a sync
         for (size_t k = 0; k < nin; ++k) {
-            if (P->in_mode[k] == NGB200_BROADCAST) { din[k] = {(void *)run.bcast[k], 1, 0, nullptr}; continue; }
-            bool soa = in[k].batch_stride == 1;
-            rc = copy_chunk(true, in[k], P->in_width[k], es, first, items, s.in[k], chunk_items, s.stream);
-            if (rc) return rc;
-            din[k] = {(void *)s.in[k], soa ? chunk_items : 1, soa ? 1 : P->in_width[k], nullptr};
+            if (P->in_mode[k] != NGB200_BROADCAST || !P->in_width[k]) continue;
+            std::vector<char> packed((size_t)P->in_width[k] * es);
+            for (int c = 0; c < P->in_width[k]; ++c) memcpy(&packed[(size_t)c * es], (char *)in[k].ptr + (size_t)c * in[k].comp_stride * es, es);
+            CU(cuMemcpyHtoDAsync(run.bcast[k], packed.data(), packed.size(), run.slots[0].stream));
+            CU(cuStreamSynchronize(run.slots[0].stream));
         }
-        for (size_t k = 0; k < nout; ++k) {
-            bool soa = out[k].batch_stride == 1;
-            dout[k] = {(void *)s.out[k], soa ? chunk_items : 1, soa ? 1 : P->out_width[k], nullptr};
+        std::vector<ngb200_operand> din(nin ? nin : 1), dout(nout);
+        int64_t chunk_index = 0;
+        for (int64_t first = 0; first < batch; first += chunk_items, ++chunk_index) {
+            HostPipe::Slot &s = run.slots[chunk_index % n_slots];
+            int64_t items = std::min(chunk_items, batch - first);
+            for (size_t k = 0; k < nin; ++k) {
+                if (P->in_mode[k] == NGB200_BROADCAST) { din[k] = {(void *)run.bcast[k], 1, 0, nullptr}; continue; }
+                bool soa = in[k].batch_stride == 1;
+                int r = copy_chunk(true, in[k], P->in_width[k], es, first, items, s.in[k], chunk_items, s.stream);
+                if (r) return r;
+                din[k] = {(void *)s.in[k], soa ? chunk_items : 1, soa ? 1 : P->in_width[k], nullptr};
+            }
+            for (size_t k = 0; k < nout; ++k) {
+                bool soa = out[k].batch_stride == 1;
+                dout[k] = {(void *)s.out[k], soa ? chunk_items : 1, soa ? 1 : P->out_width[k], nullptr};
+            }
+            int r = ngb200_program_launch(P, din.data(), dout.data(), params, items, s.stream);
+            if (r) return r;
+            for (size_t k = 0; k < nout; ++k) {
+                r = copy_chunk(false, out[k], P->out_width[k], es, first, items, s.out[k], chunk_items, s.stream);
+                if (r) return r;
+            }
         }
-        rc = ngb200_program_launch(P, din.data(), dout.data(), params, items, s.stream);
-        if (rc) return rc;
-        for (size_t k = 0; k < nout; ++k) {
-            rc = copy_chunk(false, out[k], P->out_width[k], es, first, items, s.out[k], chunk_items, s.stream);
-            if (rc) return rc;
-        }
+        return NGB200_OK;
+    };
+    rc = body();
+    const std::string first_error = rc ? g_err : std::string();
+    int sync_rc = NGB200_OK;
+    for (HostPipe::Slot &s : run.slots) {
+        CUresult r = g_drv.p_cuStreamSynchronize(s.stream);
+        if (r != CUDA_SUCCESS && !sync_rc) sync_rc = cu_fail(r, "cuStreamSynchronize");
     }
-    for (HostPipe::Slot &s : run.slots) CU(cuStreamSynchronize(s.stream));
-    return NGB200_OK;
+    if (rc) { g_err = first_error; return rc; }
+    return sync_rc;
+}
+
+// Raw-copy control of the host path (bench.py `e2e.host_ceiling_points_s`): the chunked, multi-stream H2D of
+// `in_bytes` and D2H of `out_bytes` that ngb200_program_run_host performs, WITHOUT a kernel in between.  What it
+// measures is the ceiling the pinned-memory / PCIe side of the box puts on any host-buffer pipeline.
+extern "C" int ngb200_host_copy_control(void *host_in, int64_t in_bytes, void *host_out, int64_t out_bytes,
+                                        int64_t chunk_bytes, int32_t streams, int32_t device) {
+    if ((in_bytes > 0 && !host_in) || (out_bytes > 0 && !host_out) || in_bytes < 0 || out_bytes < 0)
+        return fail(NGB200_ERR_INVALID, "bad argument");
+    int rc = need_driver();
+    if (rc) return rc;
+    int dev;
+    rc = current_device(&dev, device);
+    if (rc) return rc;
+    if (chunk_bytes <= 0) chunk_bytes = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 128) * (1 << 20) / 2;   // in + out = one pipeline chunk
+    if (streams <= 0) streams = env_int("NGB200_HOST_STREAMS", 4);
+    struct Slot { CUstream s = nullptr; CUdeviceptr din = 0, dout = 0; };
+    static std::mutex mu;
+    static std::vector<Slot> slots;
+    static int64_t slot_bytes = 0;
+    static int slot_dev = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    auto release = [&]() {
+        for (Slot &q : slots) {
+            if (q.din) g_drv.p_cuMemFree(q.din);
+            if (q.dout) g_drv.p_cuMemFree(q.dout);
+            if (q.s) g_drv.p_cuStreamDestroy(q.s);
+        }
+        slots.clear();
+        slot_bytes = 0;
+        slot_dev = -1;
+    };
+    if (slot_dev != dev || slot_bytes != chunk_bytes || (int)slots.size() != streams) {
+        release();
+        slots.resize(streams);
+        auto build = [&]() -> int {
+            for (Slot &q : slots) {
+                CU(cuStreamCreate(&q.s, CU_STREAM_NON_BLOCKING));
+                CU(cuMemAlloc(&q.din, (size_t)chunk_bytes));
+                CU(cuMemAlloc(&q.dout, (size_t)chunk_bytes));
+            }
+            return NGB200_OK;
+        };
+        rc = build();
+        if (rc) { release(); return rc; }
+        slot_bytes = chunk_bytes;
+        slot_dev = dev;
+    }
+    auto body = [&]() -> int {
+        const int64_t total = std::max(in_bytes, out_bytes);
+        int64_t k = 0;
+        for (int64_t off = 0; off < total; off += chunk_bytes, ++k) {
+            Slot &q = slots[k % streams];
+            if (off < in_bytes) CU(cuMemcpyHtoDAsync(q.din, (char *)host_in + off, (size_t)std::min(chunk_bytes, in_bytes - off), q.s));
+            if (off < out_bytes) CU(cuMemcpyDtoHAsync((char *)host_out + off, q.dout, (size_t)std::min(chunk_bytes, out_bytes - off), q.s));
+        }
+        return NGB200_OK;
+    };
+    rc = body();
+    const std::string first_error = rc ? g_err : std::string();
+    for (Slot &q : slots) g_drv.p_cuStreamSynchronize(q.s);
+    if (rc) g_err = first_error;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -75,6 +75,10 @@ def _load():
         'ngb200_program_source': (C.c_char_p, [vp]),
         'ngb200_program_launch': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(C.c_double), i64, vp]),
         'ngb200_program_run_host': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(C.c_double), i64, i32, i64]),
+        'ngb200_host_copy_control': (i32, [vp, i64, vp, i64, i64, i32, i32]),
+        'ngb200_plan_create': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), i64, C.POINTER(vp)]),
+        'ngb200_plan_launch': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_double), vp]),
+        'ngb200_plan_destroy': (None, [vp]),
         'ngb200_host_alloc': (i32, [C.POINTER(vp), i64]),
         'ngb200_host_free': (i32, [vp]),
         'ngb200_fill_normal': (i32, [vp, i64, u64, u64, C.c_double, i32, vp]),

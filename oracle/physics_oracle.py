@@ -181,7 +181,8 @@ def from_arrays(arrays, dtype, n_chains=1, rate=None):
     nb = arrays['init/motor'].shape[0]
     bodies = Body(
         O.MV(alg, alg.subspace('even_grade'), rep(arrays['init/motor'])),
-        O.MV(alg, biv, rep(arrays['init/rate'] if rate is None else rate)),
+        O.MV(alg, biv, rep(arrays['init/rate']) if rate is None else
+             (np.asarray(rate, dtype=dtype, order='F') if len(rate) == nb * n_chains else rep(rate))),
         O.MV(alg, alg.subspace('antivector'), rep(arrays['init/first_moment'])),
         DenseOp(alg, rep(arrays['init/inertia']), biv, abiv),
         DenseOp(alg, rep(arrays['init/inertia_inv']), abiv, biv),
