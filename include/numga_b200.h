@@ -193,6 +193,76 @@ int ngb200_plan_launch(ngb200_plan *plan, void *const *input_ptrs, void *const *
                        void *stream);
 void ngb200_plan_destroy(ngb200_plan *plan);
 
+/* ---- pipelines: several programs fused into ONE kernel with on-chip exchange ----------------------------------
+ * Replaces a CHAIN of operator applications with neighbour coupling that the reference runs as hundreds of array
+ * passes (numga/examples/physics/core.py:80-88 `Body.integrate`: pre_integrate -> Constraint.apply per colour set
+ * -> post_integrate -> Constraint.v_apply per colour set; 174 launches per sub-step).
+ * Items are grouped into TILES: tile t holds items [t * items_per_tile[d], (t + 1) * items_per_tile[d]) of every
+ * item domain d (e.g. bodies, constraints of colour set 0, constraints of colour set 1) and is processed by one CTA.
+ * A phase is a straight-line program over the items of one domain; its operands are bound to GLOBAL arrays (HBM;
+ * item i of the domain, or row index[i] through an int64 index operand = gather / scatter) or to SHARED buffers
+ * (on-chip for the life of the tile, component-major; item i, or row index[i] - tile * items_per_tile of the
+ * buffer's domain, which must fall inside the tile).  Phases are separated by CTA barriers; phases
+ * [loop_begin, loop_end) repeat `repeat` times per launch.  Scatter destinations must be unique per phase. */
+#define NGB200_BIND_GLOBAL 0
+#define NGB200_BIND_SHARED 1
+
+typedef struct ngb200_bind {
+    int32_t kind;  /* NGB200_BIND_GLOBAL | NGB200_BIND_SHARED */
+    int32_t slot;  /* global operand number | shared buffer number */
+    int32_t index; /* -1: addressed by the item number; else the global operand number of an int64 index array over
+                      the phase's domain */
+} ngb200_bind;
+
+typedef struct ngb200_phase_desc {
+    ngb200_program_desc program; /* input_mode / output_mode / vec are ignored: addressing comes from the bindings */
+    int32_t domain;
+    const ngb200_bind *inputs;   /* program.n_inputs entries  */
+    const ngb200_bind *outputs;  /* program.n_outputs entries */
+} ngb200_phase_desc;
+
+typedef struct ngb200_pipeline_desc {
+    int32_t dtype;
+    uint32_t flags;
+    int32_t n_domains;
+    const int32_t *items_per_tile;  /* per domain, 1..1024 */
+    int32_t n_globals;
+    const int32_t *global_width;    /* components (ignored for index arrays) */
+    const int32_t *global_domain;   /* item domain of the array; -1 = one multivector shared by all items (read-only) */
+    const int32_t *global_is_index; /* 1: int64 index array (ngb200_operand.ptr points at int64 data) */
+    int32_t n_shared;
+    const int32_t *shared_width;
+    const int32_t *shared_domain;
+    int32_t n_phases;
+    const ngb200_phase_desc *phases;
+    int32_t loop_begin, loop_end;
+    int32_t n_params;               /* runtime scalars shared by all phases */
+    int32_t threads_per_tile;       /* 0 = automatic */
+} ngb200_pipeline_desc;
+
+typedef struct ngb200_pipeline ngb200_pipeline;
+
+typedef struct ngb200_pipeline_info {
+    int32_t n_instr;          /* live instructions, all phases */
+    int32_t threads_per_tile;
+    int32_t min_blocks;       /* __launch_bounds__ minimum CTAs per SM */
+    int32_t regs;             /* registers per thread (0 until loaded on a device) */
+    int32_t grid;             /* persistent grid size (0 until loaded) */
+    int32_t cache_hit;
+    int64_t shared_bytes;     /* dynamic shared memory per CTA */
+    int64_t spill_bytes;      /* ptxas spill stores (0 when the cubin came from the cache) */
+    int64_t local_bytes;      /* local memory per thread reported by the driver */
+} ngb200_pipeline_info;
+
+int ngb200_pipeline_create(const ngb200_pipeline_desc *desc, ngb200_pipeline **out);
+void ngb200_pipeline_destroy(ngb200_pipeline *pipe);
+int ngb200_pipeline_get_info(const ngb200_pipeline *pipe, ngb200_pipeline_info *info);
+const char *ngb200_pipeline_source(const ngb200_pipeline *pipe);
+/* globals: one operand per global array (ptr, comp_stride; batch_stride must be 1; index arrays: ptr only).
+ * domain_items: total item count per domain; n_tiles CTAs' worth of tiles are processed. Asynchronous on `stream`. */
+int ngb200_pipeline_launch(ngb200_pipeline *pipe, const ngb200_operand *globals, const int64_t *domain_items,
+                           int64_t n_tiles, int32_t repeat, const double *params, void *stream);
+
 int ngb200_host_alloc(void **ptr, int64_t bytes);
 int ngb200_host_free(void *ptr);
 

@@ -27,5 +27,32 @@ def build(force=False, verbose=True):
     return LIB
 
 
+FAST_SRC = os.path.join(HERE, 'csrc', 'fastcall.cpp')
+FAST_NAME = '_ngb200_fast'
+
+
+def fast_path():
+    return os.path.join(HERE, FAST_NAME + '.so')
+
+
+def build_fast(force=False, verbose=False):
+    """The eager fast path (csrc/fastcall.cpp): a small torch C++ extension (host code only; it calls the CUDA
+    library through function pointers), built in-tree with torch.utils.cpp_extension so that it travels to the GPU
+    box next to libnumga_b200.so."""
+    out = fast_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(FAST_SRC):
+        return out
+    import shutil
+    from torch.utils.cpp_extension import load
+    bdir = os.path.join(HERE, '_fastbuild')
+    os.makedirs(bdir, exist_ok=True)
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    load(name=FAST_NAME, sources=[FAST_SRC], build_directory=bdir, extra_cflags=['-O2'], with_cuda=True, verbose=verbose,
+         is_python_module=False)
+    shutil.copyfile(os.path.join(bdir, FAST_NAME + '.so'), out)
+    return out
+
+
 if __name__ == '__main__':
     build(force='--force' in sys.argv)
+    build_fast(force='--force' in sys.argv)

@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -67,7 +68,7 @@ extern "C" int64_t ngb200_launch_count(void) { return g_launches.load(); }
 #define DRV_FUNCS(X)                                                                              \
     X(cuInit) X(cuGetErrorString) X(cuCtxGetCurrent) X(cuCtxSetCurrent) X(cuCtxGetDevice)         \
     X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuModuleLoadData) X(cuModuleUnload) \
-    X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute) X(cuFuncSetAttribute)                                \
+    X(cuModuleGetFunction) X(cuLaunchKernel) X(cuFuncGetAttribute) X(cuFuncSetAttribute)          \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemAlloc) X(cuMemFree)                     \
     X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuStreamCreate)                \
     X(cuStreamSynchronize) X(cuStreamDestroy) X(cuMemAllocHost) X(cuMemFreeHost)
@@ -248,6 +249,11 @@ struct Gen {
     int max_live = 0;         // peak number of simultaneously live per-item values (see analyse)
     std::vector<int> order;   // emission order of the varying, non-input values of the body
     bool faithful_order = true;    // true: emit in IR order; false: input-frontier order (see analyse)
+    // names used by the emitted uniform / body functions; a pipeline (several programs in one kernel) gives every
+    // phase its own suffix and maps broadcast inputs onto its own parameter block
+    std::string suffix;                       // "" -> ngb_uniform / ngb_body
+    std::string params_type = "Params";
+    std::vector<std::string> bcast_ref;       // per input k: "p.in[k]"-like expression with .ptr / .cs
 
     explicit Gen(const ngb200_program &p)
         : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {
@@ -525,17 +531,79 @@ struct Gen {
         return NGB200_OK;
     }
 
-    std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform, bool pair) {
-        plan_contraction();
-        const int n = (int)P.instr.size();
-        const int nin = (int)P.in_width.size(), nout = (int)P.out_width.size();
+    std::string bref(int k) const {
+        if (k < (int)bcast_ref.size() && !bcast_ref[k].empty()) return bcast_ref[k];
+        return "p.in[" + std::to_string(k) + "]";
+    }
+
+    // typedefs, access macros and small device helpers shared by every kernel of a translation unit
+    void emit_prelude(std::string &s, int vec, int ldmode, int stmode, bool pair) const {
         const char *T = f64 ? "double" : "float";
         const char *VT = f64 ? "double2" : (vec == 2 ? "float2" : "float4");
-        static const char *lane[4] = {"x", "y", "z", "w"};
-        std::string s;
         appendf(s, "// numga_b200 generated kernel (dtype %s, %s, vec %d%s)\n", T, faithful ? "faithful" : "fast", vec,
                 pair ? ", packed f32x2" : "");
         appendf(s, "typedef %s T;\ntypedef %s VT;\n", T, VT);
+        if (f64)
+            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysign(1.7976931348623157e308, a) : a); }\n";
+        else
+            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysignf(3.4028234663852886e38f, a) : a); }\n";
+        if (approx) {
+            s += "__device__ __forceinline__ float ngb_rcp(float a) { float r; asm(\"rcp.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+            s += "__device__ __forceinline__ float ngb_sqrt(float a) { float r; asm(\"sqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+            s += "__device__ __forceinline__ float ngb_rsqrt(float a) { float r; asm(\"rsqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
+        }
+        const char *ld = ldmode == 0 ? "*" : ldmode == 1 ? "__ldg" : ldmode == 2 ? "__ldcs" : "__ldlu";
+        appendf(s, "#define NGB_LD(p) %s(p)\n", ld);
+        if (stmode == 0) s += "#define NGB_ST(p, v) (*(p) = (v))\n";
+        else appendf(s, "#define NGB_ST(p, v) %s((p), (v))\n", stmode == 1 ? "__stcs" : stmode == 2 ? "__stcg" : "__stwt");
+    }
+
+    // values that depend only on broadcast operands / constants / launch scalars: evaluated once per thread
+    void emit_uniform(std::string &s, int *nl, int *nu) const {
+        const int n = (int)P.instr.size();
+        appendf(s, "__device__ __forceinline__ void ngb_uniform%s(const %s& p, T (&u)[%d]) {\n", suffix.c_str(),
+                params_type.c_str(), NU > 0 ? NU : 1);
+        for (int v = 0; v < n; ++v) {
+            if (!live[v] || !uniform[v]) continue;
+            const ngb200_instr &I = P.instr[v];
+            if (I.op == NGB200_OP_CONST) continue;
+            ++*nl; ++*nu;
+            if (I.op == NGB200_OP_INPUT)
+                appendf(s, "  const T q%d = __ldg(%s.ptr + %dLL * %s.cs);\n", v, bref(I.a).c_str(), I.b, bref(I.a).c_str());
+            else if (I.op == NGB200_OP_PARAM)
+                appendf(s, "  const T q%d = (T)p.scal[%d];\n", v, I.a);
+            else
+                appendf(s, "  const T q%d = %s;\n", v, expr(v, false).c_str());
+            if (uslot[v] >= 0) appendf(s, "  u[%d] = q%d;\n", uslot[v], v);
+        }
+        s += "}\n";
+    }
+
+    // the per-item straight-line body
+    void emit_body(std::string &s, int *nl, std::vector<int> *stored_out = nullptr) const {
+        appendf(s, "__device__ __forceinline__ void ngb_body%s(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
+                suffix.c_str(), NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
+        for (int v : order) {
+            ++*nl;
+            if (fused_into[v] >= 0) continue;      // this multiply lives inside the FMA of its consumer
+            appendf(s, "  const T r%d = %s;\n", v, expr(v, true).c_str());
+        }
+        std::vector<int> stored(NY > 0 ? NY : 1, -1);
+        for (const ngb200_store &st : P.stores) stored[yoff[st.operand] + st.component] = st.value;
+        for (int j = 0; j < NY; ++j) {
+            if (stored[j] >= 0) appendf(s, "  y[%d] = %s;\n", j, ref(stored[j], true).c_str());
+            else appendf(s, "  y[%d] = T(0);\n", j);
+        }
+        s += "}\n";
+        if (stored_out) *stored_out = stored;
+    }
+
+    std::string generate(int vec, int ldmode, int stmode, int *n_live, int *n_uniform, bool pair) {
+        plan_contraction();
+        const int nin = (int)P.in_width.size(), nout = (int)P.out_width.size();
+        static const char *lane[4] = {"x", "y", "z", "w"};
+        std::string s;
+        emit_prelude(s, vec, ldmode, stmode, pair);
         appendf(s, "#define NGB_V %d\n#define NGB_TPB %d\n", vec, P.tpb);
         // Grid-stride index arithmetic with the run-time blockDim.x instead of the compile-time CTA size: same
         // instruction mix, but ptxas lands on a different register allocation (123 vs 121 registers for CGA full x
@@ -553,53 +621,11 @@ struct Gen {
         else s += "struct Operand { T* ptr; long long cs; long long bs; const long long* index; };\n";
         appendf(s, "struct Params { Operand in[%d]; Operand out[%d]; double scal[%d]; long long n; };\n",
                 nin > 0 ? nin : 1, nout > 0 ? nout : 1, P.n_params > 0 ? P.n_params : 1);
-        if (f64)
-            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysign(1.7976931348623157e308, a) : a); }\n";
-        else
-            s += "__device__ __forceinline__ T ngb_nan_to_num(T a, T v) { return a != a ? v : (isinf(a) ? copysignf(3.4028234663852886e38f, a) : a); }\n";
-        if (approx) {
-            s += "__device__ __forceinline__ float ngb_rcp(float a) { float r; asm(\"rcp.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
-            s += "__device__ __forceinline__ float ngb_sqrt(float a) { float r; asm(\"sqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
-            s += "__device__ __forceinline__ float ngb_rsqrt(float a) { float r; asm(\"rsqrt.approx.ftz.f32 %0, %1;\" : \"=f\"(r) : \"f\"(a)); return r; }\n";
-        }
-        const char *ld = ldmode == 0 ? "*" : ldmode == 1 ? "__ldg" : ldmode == 2 ? "__ldcs" : "__ldlu";
-        appendf(s, "#define NGB_LD(p) %s(p)\n", ld);
-        if (stmode == 0) s += "#define NGB_ST(p, v) (*(p) = (v))\n";
-        else appendf(s, "#define NGB_ST(p, v) %s((p), (v))\n", stmode == 1 ? "__stcs" : stmode == 2 ? "__stcg" : "__stwt");
 
-        // ---- uniform preamble -------------------------------------------------------------
         int nl = 0, nu = 0;
-        appendf(s, "__device__ __forceinline__ void ngb_uniform(const Params& p, T (&u)[%d]) {\n", NU > 0 ? NU : 1);
-        for (int v = 0; v < n; ++v) {
-            if (!live[v] || !uniform[v]) continue;
-            const ngb200_instr &I = P.instr[v];
-            if (I.op == NGB200_OP_CONST) continue;
-            ++nl; ++nu;
-            if (I.op == NGB200_OP_INPUT)
-                appendf(s, "  const T q%d = __ldg(p.in[%d].ptr + %dLL * p.in[%d].cs);\n", v, I.a, I.b, I.a);
-            else if (I.op == NGB200_OP_PARAM)
-                appendf(s, "  const T q%d = (T)p.scal[%d];\n", v, I.a);
-            else
-                appendf(s, "  const T q%d = %s;\n", v, expr(v, false).c_str());
-            if (uslot[v] >= 0) appendf(s, "  u[%d] = q%d;\n", uslot[v], v);
-        }
-        s += "}\n";
-
-        // ---- per-item body ----------------------------------------------------------------
-        appendf(s, "__device__ __forceinline__ void ngb_body(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
-                NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
-        for (int v : order) {
-            ++nl;
-            if (fused_into[v] >= 0) continue;      // this multiply lives inside the FMA of its consumer
-            appendf(s, "  const T r%d = %s;\n", v, expr(v, true).c_str());
-        }
-        std::vector<int> stored(NY > 0 ? NY : 1, -1);
-        for (const ngb200_store &st : P.stores) stored[yoff[st.operand] + st.component] = st.value;
-        for (int j = 0; j < NY; ++j) {
-            if (stored[j] >= 0) appendf(s, "  y[%d] = %s;\n", j, ref(stored[j], true).c_str());
-            else appendf(s, "  y[%d] = T(0);\n", j);
-        }
-        s += "}\n";
+        emit_uniform(s, &nl, &nu);
+        std::vector<int> stored;
+        emit_body(s, &nl, &stored);
         *n_live = nl;
         *n_uniform = nu;
 
@@ -1544,6 +1570,403 @@ extern "C" int ngb200_plan_launch(ngb200_plan *pl, void *const *in_ptrs, void *c
         return plan_shoot(pl, pl->vec_tail, in_ptrs, out_ptrs, params, s);
     }
     return plan_shoot(pl, pl->scalar, in_ptrs, out_ptrs, params, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// pipelines: several programs in ONE kernel, exchanging values through shared memory
+// ------------------------------------------------------------------------------------------
+// A pipeline runs a sequence of PHASES over TILES.  Every phase is a straight-line program over the items of one
+// item domain (e.g. "bodies" or "constraints of colour set 0"); tile t holds items [t*ipt[d], (t+1)*ipt[d]) of every
+// domain d and is processed by one CTA.  Operands of a phase are bound either to a GLOBAL array (read / written in
+// HBM, optionally through an int64 index array = gather / scatter) or to a SHARED buffer that lives in the CTA's
+// shared memory for the whole tile (component-major [width][ipt]), optionally through an index array whose entries
+// must fall inside the tile.  Phases are separated by __syncthreads(); a contiguous range of phases can be repeated
+// (run-time count).  This is what lets a chain of dependent data-parallel steps with neighbour coupling (the
+// rigid-body sub-step: integrate -> relax constraint colour sets -> update rates) touch HBM once per launch.
+struct PipePhase {
+    std::unique_ptr<ngb200_program> prog;
+    int domain = 0;
+    std::vector<ngb200_bind> in, out;
+};
+
+struct PipeLoaded {
+    std::atomic<int> ready{0};
+    CUmodule mod = nullptr;
+    CUfunction f = nullptr;
+    int regs = 0, grid = 0;
+    size_t local_bytes = 0;
+};
+
+struct ngb200_pipeline {
+    int dtype = 0;
+    uint32_t flags = 0;
+    std::vector<int32_t> ipt, gwidth, gdomain, gindex, swidth, sdomain;
+    std::vector<int> gslot;                   // global operand -> slot among value operands or among index operands
+    std::vector<PipePhase> phases;
+    int loop_begin = 0, loop_end = 0, n_params = 0;
+    int tpb = 128, minb = 1;
+    int n_value_globals = 0, n_index_globals = 0;
+    size_t smem = 0, param_bytes = 0;
+    std::vector<size_t> soff;                 // element offset of every shared buffer
+    std::string source, hash;
+    std::vector<char> cubin;
+    bool cache_hit = false;
+    long spill = 0;
+    int n_live = 0;
+    std::mutex mu;
+    PipeLoaded loaded[kMaxDevices];
+};
+
+static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::string *err) {
+    const bool f64 = Q.dtype == NGB200_F64;
+    const int es = f64 ? 8 : 4;
+    std::string s;
+    std::vector<std::unique_ptr<Gen>> gens;
+    int max_need = 0, total_nu = 0;
+    Q.n_live = 0;
+    for (size_t k = 0; k < Q.phases.size(); ++k) {
+        PipePhase &ph = Q.phases[k];
+        gens.emplace_back(new Gen(*ph.prog));
+        Gen &g = *gens.back();
+        g.faithful_order = ir_order;
+        if (g.analyse() != NGB200_OK) { *err = g_err; return ""; }
+        g.plan_contraction();
+        g.suffix = "_" + std::to_string(k);
+        g.params_type = "PParams";
+        g.bcast_ref.assign(ph.in.size(), "");
+        for (size_t j = 0; j < ph.in.size(); ++j)
+            if (ph.prog->in_mode[j] == NGB200_BROADCAST) g.bcast_ref[j] = "p.g[" + std::to_string(Q.gslot[ph.in[j].slot]) + "]";
+        const int need = g.max_live * (f64 ? 2 : 1) + 24;
+        if (need > max_need) max_need = need;
+        total_nu += g.NU;
+    }
+    max_need += total_nu * (f64 ? 2 : 1);
+    int minb = 65536 / (Q.tpb * (max_need > 32 ? max_need : 32));
+    Q.minb = minb < 1 ? 1 : (minb > 8 ? 8 : minb);
+    if (env_int("NGB200_PIPE_MINB", 0) > 0) Q.minb = env_int("NGB200_PIPE_MINB", 0);
+    gens[0]->emit_prelude(s, 1, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), false);
+    appendf(s, "#define NGB_TPB %d\n", Q.tpb);
+    s += "struct PG { T* ptr; long long cs; };\n";
+    appendf(s, "struct PParams { PG g[%d]; const long long* idx[%d]; double scal[%d]; long long n[%d]; long long n_tiles; int repeat; };\n",
+            Q.n_value_globals > 0 ? Q.n_value_globals : 1, Q.n_index_globals > 0 ? Q.n_index_globals : 1,
+            Q.n_params > 0 ? Q.n_params : 1, (int)Q.ipt.size());
+    for (size_t k = 0; k < Q.phases.size(); ++k) {
+        int nl = 0, nu = 0;
+        gens[k]->emit_uniform(s, &nl, &nu);
+        gens[k]->emit_body(s, &nl);
+        Q.n_live += nl;
+    }
+    if (Q.minb > 1 && 65536 / (Q.tpb * Q.minb) < 255) appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB, %d) ngb_pipeline(const PParams p) {\n", Q.minb);
+    else s += "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_pipeline(const PParams p) {\n";
+    s += "  extern __shared__ __align__(16) unsigned char ngb_raw[];\n  T* const sm = reinterpret_cast<T*>(ngb_raw);\n";
+    for (size_t k = 0; k < Q.phases.size(); ++k)
+        appendf(s, "  T u%zu[%d]; ngb_uniform_%zu(p, u%zu);\n", k, gens[k]->NU > 0 ? gens[k]->NU : 1, k, k);
+    s += "  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {\n";
+    auto emit_phase = [&](size_t k, const char *ind) {
+        PipePhase &ph = Q.phases[k];
+        Gen &g = *gens[k];
+        const int d = ph.domain, ipt = Q.ipt[d];
+        appendf(s, "%s{ // phase %zu: domain %d, %d items per tile\n", ind, k, d, ipt);
+        if (ipt <= Q.tpb) appendf(s, "%s  const int i = threadIdx.x;\n%s  if (i < %d) {\n", ind, ind, ipt);
+        else appendf(s, "%s  for (int i = threadIdx.x; i < %d; i += NGB_TPB) {\n", ind, ipt);
+        appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    if (gi < p.n[%d]) {\n", ind, ipt, ind, d);
+        appendf(s, "%s      T x[%d]; T y[%d];\n", ind, g.NX > 0 ? g.NX : 1, g.NY > 0 ? g.NY : 1);
+        // row of an indexed access: global arrays use the index value itself, shared buffers the tile-local part
+        std::map<std::pair<int, int>, std::string> rows;
+        auto row_of = [&](const ngb200_bind &b) -> std::string {
+            const bool shared = b.kind == NGB200_BIND_SHARED;
+            const int target = shared ? Q.sdomain[b.slot] : -1;
+            auto key = std::make_pair(b.index, target);
+            auto it = rows.find(key);
+            if (it != rows.end()) return it->second;
+            std::string name = "row" + std::to_string(rows.size());
+            if (shared)
+                appendf(s, "%s      const int %s = (int)(p.idx[%d][gi] - tile * %dLL);\n", ind, name.c_str(), Q.gslot[b.index], Q.ipt[target]);
+            else
+                appendf(s, "%s      const long long %s = p.idx[%d][gi];\n", ind, name.c_str(), Q.gslot[b.index]);
+            rows[key] = name;
+            return name;
+        };
+        auto address = [&](const ngb200_bind &b, int c) -> std::string {
+            char buf[256];
+            if (b.kind == NGB200_BIND_SHARED) {
+                const int w = Q.ipt[Q.sdomain[b.slot]];
+                std::string r = b.index >= 0 ? row_of(b) : std::string("i");
+                snprintf(buf, sizeof buf, "sm + %zu + %d * %d + %s", Q.soff[b.slot], c, w, r.c_str());
+            } else {
+                std::string r = b.index >= 0 ? row_of(b) : std::string("gi");
+                snprintf(buf, sizeof buf, "p.g[%d].ptr + %dLL * p.g[%d].cs + %s", Q.gslot[b.slot], c, Q.gslot[b.slot], r.c_str());
+            }
+            return buf;
+        };
+        std::vector<char> used(g.NX > 0 ? g.NX : 1, 0);
+        for (size_t v = 0; v < ph.prog->instr.size(); ++v) {
+            const ngb200_instr &I = ph.prog->instr[v];
+            if (I.op == NGB200_OP_INPUT && g.live[v] && !g.uniform[v]) used[g.xoff[I.a] + I.b] = 1;
+        }
+        for (size_t j = 0; j < ph.in.size(); ++j) {
+            if (ph.prog->in_mode[j] == NGB200_BROADCAST) continue;
+            for (int c = 0; c < ph.prog->in_width[j]; ++c) {
+                if (!used[g.xoff[j] + c]) continue;          // structurally dead component: never loaded
+                std::string a = address(ph.in[j], c);
+                if (ph.in[j].kind == NGB200_BIND_SHARED) appendf(s, "%s      x[%d] = *(%s);\n", ind, g.xoff[j] + c, a.c_str());
+                else appendf(s, "%s      x[%d] = NGB_LD(%s);\n", ind, g.xoff[j] + c, a.c_str());
+            }
+        }
+        appendf(s, "%s      ngb_body_%zu(x, u%zu, y);\n", ind, k, k);
+        for (size_t j = 0; j < ph.out.size(); ++j)
+            for (int c = 0; c < ph.prog->out_width[j]; ++c) {
+                std::string a = address(ph.out[j], c);
+                if (ph.out[j].kind == NGB200_BIND_SHARED) appendf(s, "%s      *(%s) = y[%d];\n", ind, a.c_str(), g.yoff[j] + c);
+                else appendf(s, "%s      NGB_ST(%s, y[%d]);\n", ind, a.c_str(), g.yoff[j] + c);
+            }
+        appendf(s, "%s    }\n%s  }\n%s}\n%s__syncthreads();\n", ind, ind, ind, ind);
+    };
+    for (int k = 0; k < Q.loop_begin; ++k) emit_phase(k, "    ");
+    if (Q.loop_end > Q.loop_begin) {
+        s += "    for (int rep = 0; rep < p.repeat; ++rep) {\n";
+        for (int k = Q.loop_begin; k < Q.loop_end; ++k) emit_phase(k, "      ");
+        s += "    }\n";
+    }
+    for (int k = Q.loop_end; k < (int)Q.phases.size(); ++k) emit_phase(k, "    ");
+    s += "  }\n}\n";
+    (void)es;
+    return s;
+}
+
+extern "C" int ngb200_pipeline_create(const ngb200_pipeline_desc *d, ngb200_pipeline **out) {
+    if (!d || !out) return fail(NGB200_ERR_INVALID, "null argument");
+    if (d->dtype != NGB200_F32 && d->dtype != NGB200_F64) return fail(NGB200_ERR_INVALID, "bad dtype %d", d->dtype);
+    if (d->n_domains < 1 || d->n_globals < 1 || d->n_shared < 0 || d->n_phases < 1 || d->n_params < 0)
+        return fail(NGB200_ERR_INVALID, "bad counts in pipeline description");
+    if (d->loop_begin < 0 || d->loop_end < d->loop_begin || d->loop_end > d->n_phases) return fail(NGB200_ERR_INVALID, "bad loop range");
+    std::unique_ptr<ngb200_pipeline> Q(new ngb200_pipeline);
+    Q->dtype = d->dtype;
+    Q->flags = d->flags;
+    Q->ipt.assign(d->items_per_tile, d->items_per_tile + d->n_domains);
+    Q->gwidth.assign(d->global_width, d->global_width + d->n_globals);
+    Q->gdomain.assign(d->global_domain, d->global_domain + d->n_globals);
+    Q->gindex.assign(d->global_is_index, d->global_is_index + d->n_globals);
+    if (d->n_shared) {
+        Q->swidth.assign(d->shared_width, d->shared_width + d->n_shared);
+        Q->sdomain.assign(d->shared_domain, d->shared_domain + d->n_shared);
+    }
+    Q->loop_begin = d->loop_begin;
+    Q->loop_end = d->loop_end;
+    Q->n_params = d->n_params;
+    int max_ipt = 0;
+    for (int v : Q->ipt) { if (v < 1 || v > 1024) return fail(NGB200_ERR_INVALID, "items per tile must be 1..1024"); max_ipt = std::max(max_ipt, v); }
+    for (int k = 0; k < d->n_globals; ++k) {
+        if (Q->gdomain[k] < -1 || Q->gdomain[k] >= d->n_domains) return fail(NGB200_ERR_INVALID, "global %d: bad domain", k);
+        Q->gslot.push_back(Q->gindex[k] ? Q->n_index_globals++ : Q->n_value_globals++);
+    }
+    const int es = esize(d->dtype);
+    size_t off = 0;
+    for (int k = 0; k < d->n_shared; ++k) {
+        if (Q->sdomain[k] < 0 || Q->sdomain[k] >= d->n_domains || Q->swidth[k] < 1) return fail(NGB200_ERR_INVALID, "shared buffer %d: bad description", k);
+        Q->soff.push_back(off);
+        off += (size_t)Q->swidth[k] * Q->ipt[Q->sdomain[k]];
+    }
+    Q->smem = off * es;
+    if (Q->smem > 227 * 1024) return fail(NGB200_ERR_INVALID, "tile needs %zu bytes of shared memory (limit 232448)", Q->smem);
+    Q->tpb = d->threads_per_tile > 0 ? d->threads_per_tile : std::min(256, (max_ipt + 31) / 32 * 32);
+    if (Q->tpb % 32 || Q->tpb > 1024) return fail(NGB200_ERR_INVALID, "threads per tile must be a multiple of 32, at most 1024");
+    Q->param_bytes = 16 * (size_t)std::max(1, Q->n_value_globals) + 8 * (size_t)std::max(1, Q->n_index_globals) +
+                     8 * (size_t)std::max(1, Q->n_params) + 8 * Q->ipt.size() + 8 + 8;
+    if (Q->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel");
+    for (int k = 0; k < d->n_phases; ++k) {
+        const ngb200_phase_desc &pd = d->phases[k];
+        const ngb200_program_desc &pp = pd.program;
+        if (pd.domain < 0 || pd.domain >= d->n_domains) return fail(NGB200_ERR_INVALID, "phase %d: bad domain", k);
+        if (pp.n_params > d->n_params) return fail(NGB200_ERR_INVALID, "phase %d: uses more scalar params than the pipeline has", k);
+        PipePhase ph;
+        ph.domain = pd.domain;
+        ph.prog.reset(new ngb200_program);
+        ngb200_program &P = *ph.prog;
+        P.dtype = d->dtype;
+        P.flags = d->flags;
+        P.in_width.assign(pp.input_width, pp.input_width + pp.n_inputs);
+        P.out_width.assign(pp.output_width, pp.output_width + pp.n_outputs);
+        P.out_mode.assign(pp.n_outputs, NGB200_VARYING);
+        P.n_params = d->n_params;
+        if (pp.n_consts) P.consts.assign(pp.consts, pp.consts + pp.n_consts);
+        if (pp.n_instr) P.instr.assign(pp.instr, pp.instr + pp.n_instr);
+        if (pp.n_stores) P.stores.assign(pp.stores, pp.stores + pp.n_stores);
+        ph.in.assign(pd.inputs, pd.inputs + pp.n_inputs);
+        ph.out.assign(pd.outputs, pd.outputs + pp.n_outputs);
+        auto check = [&](const ngb200_bind &b, int width, bool is_out, int j) -> int {
+            const char *what = is_out ? "output" : "input";
+            if (b.kind == NGB200_BIND_SHARED) {
+                if (b.slot < 0 || b.slot >= d->n_shared) return fail(NGB200_ERR_INVALID, "phase %d %s %d: bad shared buffer", k, what, j);
+                if (Q->swidth[b.slot] != width) return fail(NGB200_ERR_INVALID, "phase %d %s %d: width %d != shared buffer width %d", k, what, j, width, Q->swidth[b.slot]);
+                if (b.index < 0 && Q->sdomain[b.slot] != pd.domain) return fail(NGB200_ERR_INVALID, "phase %d %s %d: direct access to a buffer of another domain", k, what, j);
+            } else if (b.kind == NGB200_BIND_GLOBAL) {
+                if (b.slot < 0 || b.slot >= d->n_globals || Q->gindex[b.slot]) return fail(NGB200_ERR_INVALID, "phase %d %s %d: bad global operand", k, what, j);
+                if (Q->gwidth[b.slot] != width) return fail(NGB200_ERR_INVALID, "phase %d %s %d: width %d != global operand width %d", k, what, j, width, Q->gwidth[b.slot]);
+                if (Q->gdomain[b.slot] < 0 && (is_out || b.index >= 0)) return fail(NGB200_ERR_INVALID, "phase %d %s %d: a broadcast operand is read-only and not indexed", k, what, j);
+                if (Q->gdomain[b.slot] >= 0 && b.index < 0 && Q->gdomain[b.slot] != pd.domain) return fail(NGB200_ERR_INVALID, "phase %d %s %d: direct access to an array of another domain", k, what, j);
+            } else return fail(NGB200_ERR_INVALID, "phase %d %s %d: bad binding kind", k, what, j);
+            if (b.index >= 0) {
+                if (b.index >= d->n_globals || !Q->gindex[b.index] || Q->gdomain[b.index] != pd.domain)
+                    return fail(NGB200_ERR_INVALID, "phase %d %s %d: index operand must be an index array over the phase's domain", k, what, j);
+            }
+            return NGB200_OK;
+        };
+        for (int j = 0; j < pp.n_inputs; ++j) {
+            int rc = check(ph.in[j], P.in_width[j], false, j);
+            if (rc) return rc;
+            const ngb200_bind &b = ph.in[j];
+            P.in_mode.push_back(b.kind == NGB200_BIND_GLOBAL && Q->gdomain[b.slot] < 0 ? NGB200_BROADCAST : NGB200_VARYING);
+        }
+        for (int j = 0; j < pp.n_outputs; ++j) {
+            int rc = check(ph.out[j], P.out_width[j], true, j);
+            if (rc) return rc;
+        }
+        Q->phases.push_back(std::move(ph));
+    }
+    const int forced = env_int("NGB200_IR_ORDER", -1);
+    std::string err;
+    Q->source = pipeline_source(*Q, forced != 0, &err);
+    if (Q->source.empty()) return fail(NGB200_ERR_INVALID, "%s", err.c_str());
+    Q->hash = hash_hex(Q->source + "|sm_100a|pipeline");
+    std::lock_guard<std::mutex> lock(g_mu);
+    const bool use_cache = !env_int("NGB200_NO_CACHE", 0);
+    std::string base = cache_dir() + "/" + Q->hash;
+    std::vector<char> marker;
+    if (use_cache && forced < 0 && read_file(base + ".alt", marker)) {       // the other emission order won last time
+        Q->source = pipeline_source(*Q, false, &err);
+        Q->hash = hash_hex(Q->source + "|sm_100a|pipeline");
+        base = cache_dir() + "/" + Q->hash;
+    }
+    if (use_cache && read_file(base + ".cubin", Q->cubin)) {
+        Q->cache_hit = true;
+        *out = Q.release();
+        return NGB200_OK;
+    }
+    std::string log;
+    int rc = nvrtc_compile(Q->source, Q->cubin, &log);
+    if (rc) return rc;
+    Q->spill = spill_bytes(log, "ngb_pipeline");
+    if (forced < 0 && Q->spill > 0 && marker.empty()) {
+        std::string src_ir = Q->source, hash_ir = Q->hash;
+        std::vector<char> cubin_ir = Q->cubin;
+        const int minb_ir = Q->minb;
+        std::string alt = pipeline_source(*Q, false, &err);
+        std::vector<char> cubin_alt;
+        std::string log_alt;
+        if (!alt.empty() && nvrtc_compile(alt, cubin_alt, &log_alt) == NGB200_OK && spill_bytes(log_alt, "ngb_pipeline") < Q->spill) {
+            Q->source = alt;
+            Q->cubin = cubin_alt;
+            Q->spill = spill_bytes(log_alt, "ngb_pipeline");
+            Q->hash = hash_hex(Q->source + "|sm_100a|pipeline");
+            write_file((cache_dir() + "/" + hash_ir + ".alt").c_str(), Q->hash.data(), Q->hash.size());
+            base = cache_dir() + "/" + Q->hash;
+        } else {
+            Q->source = src_ir;
+            Q->cubin = cubin_ir;
+            Q->minb = minb_ir;
+        }
+    }
+    write_file(base + ".cubin", Q->cubin.data(), Q->cubin.size());
+    if (env_int("NGB200_CACHE_SOURCES", 0)) write_file(base + ".cu", Q->source.data(), Q->source.size());
+    *out = Q.release();
+    return NGB200_OK;
+}
+
+extern "C" void ngb200_pipeline_destroy(ngb200_pipeline *Q) {
+    if (!Q) return;
+    if (g_drv.ok) {
+        for (int d = 0; d < kMaxDevices; ++d) {
+            PipeLoaded &L = Q->loaded[d];
+            if (!L.ready.load() || !L.mod) continue;
+            CUcontext prev = nullptr, ctx = nullptr;
+            CUdevice dev;
+            if (g_drv.p_cuCtxGetCurrent(&prev) != CUDA_SUCCESS) continue;
+            if (g_drv.p_cuDeviceGet(&dev, d) != CUDA_SUCCESS || g_drv.p_cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS) continue;
+            g_drv.p_cuCtxSetCurrent(ctx);
+            g_drv.p_cuModuleUnload(L.mod);
+            g_drv.p_cuCtxSetCurrent(prev);
+        }
+    }
+    delete Q;
+}
+
+extern "C" const char *ngb200_pipeline_source(const ngb200_pipeline *Q) { return Q ? Q->source.c_str() : ""; }
+
+extern "C" int ngb200_pipeline_get_info(const ngb200_pipeline *Q, ngb200_pipeline_info *info) {
+    if (!Q || !info) return fail(NGB200_ERR_INVALID, "null argument");
+    memset(info, 0, sizeof *info);
+    info->n_instr = Q->n_live;
+    info->threads_per_tile = Q->tpb;
+    info->min_blocks = Q->minb;
+    info->shared_bytes = (int64_t)Q->smem;
+    info->cache_hit = Q->cache_hit;
+    info->spill_bytes = (int64_t)Q->spill;
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (Q->loaded[d].ready.load()) { info->regs = Q->loaded[d].regs; info->grid = Q->loaded[d].grid; info->local_bytes = (int64_t)Q->loaded[d].local_bytes; break; }
+    return NGB200_OK;
+}
+
+extern "C" int ngb200_pipeline_launch(ngb200_pipeline *Q, const ngb200_operand *globals, const int64_t *domain_items,
+                                      int64_t n_tiles, int32_t repeat, const double *params, void *stream) {
+    if (!Q || !globals || !domain_items) return fail(NGB200_ERR_INVALID, "null argument");
+    if (n_tiles < 0 || repeat < 0) return fail(NGB200_ERR_INVALID, "negative tile / repeat count");
+    if (Q->n_params > 0 && !params) return fail(NGB200_ERR_INVALID, "pipeline needs %d scalar params", Q->n_params);
+    int rc = need_driver();
+    if (rc) return rc;
+    if (n_tiles == 0) return NGB200_OK;
+    int dev = 0;
+    rc = current_device(&dev, -1);
+    if (rc) return rc;
+    if (dev < 0 || dev >= kMaxDevices) return fail(NGB200_ERR_CUDA, "device ordinal %d not supported", dev);
+    PipeLoaded &L = Q->loaded[dev];
+    if (!L.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(Q->mu);
+        if (!L.ready.load()) {
+            CU(cuModuleLoadData(&L.mod, Q->cubin.data()));
+            CU(cuModuleGetFunction(&L.f, L.mod, "ngb_pipeline"));
+            CU(cuFuncGetAttribute(&L.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, L.f));
+            int lb = 0;
+            CU(cuFuncGetAttribute(&lb, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, L.f));
+            L.local_bytes = (size_t)lb;
+            if (Q->smem > 48 * 1024) CU(cuFuncSetAttribute(L.f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)Q->smem));
+            int sms = 0, nb = 0;
+            CU(cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.f, Q->tpb, Q->smem));
+            L.grid = sms * (nb > 0 ? nb : 1);
+            L.ready.store(1, std::memory_order_release);
+        }
+    }
+    const size_t ng = Q->gwidth.size();
+    for (size_t k = 0; k < ng; ++k) {
+        if (!globals[k].ptr) return fail(NGB200_ERR_INVALID, "global operand %zu: null pointer", k);
+        if (!Q->gindex[k] && Q->gdomain[k] >= 0 && globals[k].batch_stride != 1)
+            return fail(NGB200_ERR_INVALID, "global operand %zu: pipelines need structure-of-arrays operands (batch stride 1)", k);
+    }
+    alignas(16) char buf[4096];
+    memset(buf, 0, Q->param_bytes);
+    char *w = buf;
+    struct PG { void *ptr; long long cs; };
+    for (size_t k = 0; k < ng; ++k)
+        if (!Q->gindex[k]) { PG g{globals[k].ptr, globals[k].comp_stride}; memcpy(w + 16 * Q->gslot[k], &g, 16); }
+    w += 16 * (size_t)std::max(1, Q->n_value_globals);
+    for (size_t k = 0; k < ng; ++k)
+        if (Q->gindex[k]) memcpy(w + 8 * Q->gslot[k], &globals[k].ptr, 8);
+    w += 8 * (size_t)std::max(1, Q->n_index_globals);
+    for (int k = 0; k < Q->n_params; ++k) memcpy(w + 8 * k, &params[k], 8);
+    w += 8 * (size_t)std::max(1, Q->n_params);
+    for (size_t k = 0; k < Q->ipt.size(); ++k) { long long v = domain_items[k]; memcpy(w + 8 * k, &v, 8); }
+    w += 8 * Q->ipt.size();
+    long long nt = n_tiles;
+    memcpy(w, &nt, 8);
+    w += 8;
+    int rp = repeat;
+    memcpy(w, &rp, 4);
+    const int64_t blocks = std::min<int64_t>(n_tiles, L.grid);
+    void *args[] = {buf};
+    CU(cuLaunchKernel(L.f, (unsigned)blocks, 1, 1, (unsigned)Q->tpb, 1, 1, (unsigned)Q->smem, (CUstream)stream, args, nullptr));
+    g_launches.fetch_add(1);
+    return NGB200_OK;
 }
 
 // ------------------------------------------------------------------------------------------

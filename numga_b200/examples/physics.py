@@ -285,3 +285,134 @@ class FusedStep:
                           bodies.inertia_inv.indexed(i0), bodies.inertia_inv.indexed(i1), c.anchors_map[0],
                           c.anchors_map[1], c.compliance, dt, out=(rate.indexed(i0), rate.indexed(i1)))
         return bodies.copy(motor=motor, rate=rate)
+
+
+def _block_structure(n_bodies, index_sets, max_block=1024):
+    """Smallest block size b such that the bodies split into n_bodies / b consecutive blocks, every constraint joins
+    two bodies of ONE block, and the constraints of every set are laid out block by block with the same count per
+    block.  Returns (b, [constraints per block per set]); raises when the system has no such structure."""
+    import torch
+    for b in range(2, min(max_block, n_bodies) + 1):
+        if n_bodies % b:
+            continue
+        n_blocks = n_bodies // b
+        per_block, ok = [], True
+        for idx in index_sets:
+            nc = int(idx.shape[1])
+            if nc % n_blocks:
+                ok = False
+                break
+            cpb = nc // n_blocks
+            blk = torch.arange(nc, device=idx.device) // cpb
+            if not bool((torch.div(idx, b, rounding_mode='floor') == blk[None, :]).all()):
+                ok = False
+                break
+            per_block.append(cpb)
+        if ok:
+            return b, per_block
+    raise ValueError('constraints do not decompose into independent blocks of <= %d consecutive bodies; use FusedStep' % max_block)
+
+
+class ChainStep:
+    """The sub-step as ONE chain-resident kernel (numga_b200/pipeline.py): a CTA owns a tile of whole chains, loads
+    motor / rate / inverse inertia into shared memory once, runs  pre -> apply per colour set -> post -> v_apply per
+    colour set  with CTA barriers in between (constraint threads read and write the two bodies they join in shared
+    memory), repeats that `unroll` times (the reference drives `unroll=10` sub-steps per frame,
+    numga/examples/physics/run_chain_numpy.py:26-30) and stores motor / rate once.  Per launch every state word
+    crosses HBM once; the per-body constants and per-constraint tables are re-read per sub-step from L2.
+
+    Needs the block structure `replicate_chains` produces (independent chains laid out one after the other); the
+    formulas are the same traced python bodies `FusedStep` uses.  `integrate(bodies, dt)` = `unroll` sub-steps of dt."""
+
+    def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0):
+        from numga_b200.pipeline import Pipeline
+        import torch
+        ctx = self.context = bodies.motor.context
+        self.sets, self.unroll = list(constraint_sets), int(unroll)
+        n_bodies = bodies.motor.shape[0]
+        block, per_block = _block_structure(n_bodies, [c.body_idx for c in self.sets])
+        if bodies_per_tile is None:
+            bodies_per_tile = 128 if ctx.dtype == torch.float32 else 64
+        k = max(1, bodies_per_tile // block)                       # whole blocks (chains) per tile
+        self.block, self.blocks_per_tile = block, k
+        S = ctx.subspace
+        names = ['body'] + [f'set{j}' for j in range(len(self.sets))]
+        pipe = Pipeline(ctx, dict(zip(names, [block * k] + [c * k for c in per_block])), threads_per_tile=threads_per_tile)
+        from numga_b200.backend import _OperatorKey
+        inv_space = _OperatorKey(bodies.inertia_inv.axes, bodies.inertia_inv.mask)
+        inertia_space = _OperatorKey(bodies.inertia.axes, bodies.inertia.mask)
+        g_motor, g_rate = pipe.array('motor', S.even_grade(), 'body'), pipe.array('rate', S.bivector(), 'body')
+        g_fm = pipe.array('first_moment', bodies.first_moment.subspace, 'body')
+        g_inertia, g_inv = pipe.array('inertia', inertia_space, 'body'), pipe.array('inertia_inv', inv_space, 'body')
+        g_damping, g_gravity = pipe.array('damping', bodies.damping.subspace, 'body'), pipe.array('gravity', bodies.gravity.subspace, 'body')
+        o_motor, o_rate = pipe.array('motor_out', S.even_grade(), 'body'), pipe.array('rate_out', S.bivector(), 'body')
+        s_motor, s_rate = pipe.buffer(S.even_grade(), 'body'), pipe.buffer(S.bivector(), 'body')
+        s_old, s_inv = pipe.buffer(S.even_grade(), 'body'), pipe.buffer(inv_space, 'body')
+        dt = pipe.param(0)
+
+        from numga_b200.pipeline import operator_values
+        pipe.phase('body', lambda m, r, inv: (m, r, operator_values(inv)), [g_motor, g_rate, g_inv], [s_motor, s_rate, s_inv])
+
+        def pre(motor, rate, first_moment, inertia, inertia_inv, damping, gravity, dt):
+            new = Body(motor, rate, first_moment, inertia, inertia_inv, damping, gravity).pre_integrate(dt)
+            return new.motor, new.rate, motor
+        pipe.phase('body', pre, [s_motor, s_rate, g_fm, g_inertia, s_inv, g_damping, g_gravity, dt], [s_motor, s_rate, s_old])
+
+        def apply(m0, m1, inv0, inv1, a0, a1, compliance, dt):
+            w0, w1 = m0 >> a0, m1 >> a1
+            forque = w0 & w1
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            s0, s1 = FusedStep._distribute(m0 << direction, m1 << direction, magnitude, inv0, inv1, compliance / (dt * dt))
+            return motor_add_step(m0, s0), motor_add_step(m1, s1)
+
+        def post(motor, old_motor, dt):
+            m = motor.normalized()
+            return m, motor_relative_step(m.reverse(), old_motor.reverse()) / dt
+
+        def v_apply(m0, m1, r0, r1, inv0, inv1, map0, map1, compliance, dt):
+            v0, v1 = m0 >> map0(r0), m1 >> map1(r1)
+            forque = -(v0 * 0.5 + v1 * -0.5)
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            s0, s1 = FusedStep._distribute(m0 << direction, m1 << direction, magnitude, inv0, inv1, compliance * 0)
+            return r0 + s0, r1 + s1
+
+        per_set = []
+        for j, c in enumerate(self.sets):
+            i0, i1 = pipe.index(f'set{j}/i0', f'set{j}'), pipe.index(f'set{j}/i1', f'set{j}')
+            a0, a1 = pipe.array(f'set{j}/a0', c.anchors.subspace, f'set{j}'), pipe.array(f'set{j}/a1', c.anchors.subspace, f'set{j}')
+            map_space = _OperatorKey(c.anchors_map.axes, c.anchors_map.mask)
+            m0, m1 = pipe.array(f'set{j}/map0', map_space, f'set{j}'), pipe.array(f'set{j}/map1', map_space, f'set{j}')
+            comp = pipe.array(f'set{j}/compliance', c.compliance.subspace, f'set{j}')
+            per_set.append((i0, i1, a0, a1, m0, m1, comp))
+        for j, (i0, i1, a0, a1, m0, m1, comp) in enumerate(per_set):
+            pipe.phase(f'set{j}', apply, [s_motor[i0], s_motor[i1], s_inv[i0], s_inv[i1], a0, a1, comp, dt], [s_motor[i0], s_motor[i1]])
+        pipe.phase('body', post, [s_motor, s_old, dt], [s_motor, s_rate])
+        for j, (i0, i1, a0, a1, m0, m1, comp) in enumerate(per_set):
+            pipe.phase(f'set{j}', v_apply, [s_motor[i0], s_motor[i1], s_rate[i0], s_rate[i1], s_inv[i0], s_inv[i1], m0, m1, comp, dt],
+                       [s_rate[i0], s_rate[i1]])
+        n_loop = 2 + 2 * len(self.sets)
+        pipe.phase('body', lambda m, r: (m, r), [s_motor, s_rate], [o_motor, o_rate])
+        self.compiled = pipe.build(loop=(1, 1 + n_loop))
+        # per-set operands never change between steps: resolved once
+        self._static = {}
+        for j, c in enumerate(self.sets):
+            self._static.update({f'set{j}/i0': c.body_idx[0].contiguous(), f'set{j}/i1': c.body_idx[1].contiguous(),
+                                 f'set{j}/a0': c.anchors[0], f'set{j}/a1': c.anchors[1],
+                                 f'set{j}/map0': c.anchors_map[0], f'set{j}/map1': c.anchors_map[1],
+                                 f'set{j}/compliance': c.compliance})
+        self._items = {f'set{j}': int(c.body_idx.shape[1]) for j, c in enumerate(self.sets)}
+        self._items['body'] = n_bodies
+
+    def integrate(self, bodies, dt):
+        from numga_b200.backend import soa_empty
+        ctx = self.context
+        n = bodies.motor.shape[0]
+        motor = ctx.mvtype(ctx, bodies.motor.subspace, soa_empty(8, (n,), ctx.dtype, ctx.device))
+        rate = ctx.mvtype(ctx, bodies.rate.subspace, soa_empty(6, (n,), ctx.dtype, ctx.device))
+        arrays = dict(self._static, motor=bodies.motor, rate=bodies.rate, first_moment=bodies.first_moment,
+                      inertia=bodies.inertia, inertia_inv=bodies.inertia_inv, damping=bodies.damping, gravity=bodies.gravity,
+                      motor_out=motor, rate_out=rate)
+        self.compiled.launch(arrays, self._items, repeat=self.unroll, params=[dt])
+        return bodies.copy(motor=motor, rate=rate)

@@ -98,11 +98,13 @@ def run_job(job):
             rt.Program.from_terms(terms, [8, 8], 8, rt.F32 if dtype == torch.float32 else rt.F64, flags=rt.FAITHFUL)
     elif kind == 'physics':
         # rigid-body physics (config 5): the generic per-method kernels and the six fused kernels of a sub-step
-        from numga_b200.examples.physics import FusedStep, setup_bodies
+        from numga_b200.examples.physics import ChainStep, FusedStep, setup_bodies
         ctx = ctx_of('x+y+z+w0', getattr(torch, arg[0]), arg[1])
         bodies, sets = setup_bodies(ctx, n_bodies=12)
         bodies.integrate(1 / 200, sets)
         FusedStep(bodies, sets).integrate(bodies, 1 / 200)
+        for bpt in (None, 84):          # the chain-resident pipeline kernel: default tile and the partial-tile test's
+            ChainStep(bodies, sets, bodies_per_tile=bpt).integrate(bodies, 1 / 200)
         bodies.kinetic_energy()
     elif kind == 'case':
         from cases import CASE_BY_NAME

@@ -52,6 +52,32 @@ class Operand(C.Structure):
                 ('inner_size', C.c_int64), ('outer_stride', C.c_int64)]
 
 
+class Bind(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('slot', C.c_int32), ('index', C.c_int32)]
+
+
+class PhaseDesc(C.Structure):
+    _fields_ = [('program', ProgramDesc), ('domain', C.c_int32), ('inputs', C.POINTER(Bind)), ('outputs', C.POINTER(Bind))]
+
+
+class PipelineDesc(C.Structure):
+    _fields_ = [
+        ('dtype', C.c_int32), ('flags', C.c_uint32),
+        ('n_domains', C.c_int32), ('items_per_tile', C.POINTER(C.c_int32)),
+        ('n_globals', C.c_int32), ('global_width', C.POINTER(C.c_int32)), ('global_domain', C.POINTER(C.c_int32)),
+        ('global_is_index', C.POINTER(C.c_int32)),
+        ('n_shared', C.c_int32), ('shared_width', C.POINTER(C.c_int32)), ('shared_domain', C.POINTER(C.c_int32)),
+        ('n_phases', C.c_int32), ('phases', C.POINTER(PhaseDesc)),
+        ('loop_begin', C.c_int32), ('loop_end', C.c_int32), ('n_params', C.c_int32), ('threads_per_tile', C.c_int32),
+    ]
+
+
+class PipelineInfo(C.Structure):
+    _fields_ = [('n_instr', C.c_int32), ('threads_per_tile', C.c_int32), ('min_blocks', C.c_int32), ('regs', C.c_int32),
+                ('grid', C.c_int32), ('cache_hit', C.c_int32), ('shared_bytes', C.c_int64), ('spill_bytes', C.c_int64),
+                ('local_bytes', C.c_int64)]
+
+
 class ProgramInfo(C.Structure):
     _fields_ = [('n_instr', C.c_int32), ('n_uniform', C.c_int32), ('vec', C.c_int32), ('regs_vec', C.c_int32),
                 ('regs_scalar', C.c_int32), ('cache_hit', C.c_int32), ('cubin_bytes', C.c_int64)]
@@ -79,6 +105,11 @@ def _load():
         'ngb200_plan_create': (i32, [vp, C.POINTER(Operand), C.POINTER(Operand), i64, C.POINTER(vp)]),
         'ngb200_plan_launch': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_double), vp]),
         'ngb200_plan_destroy': (None, [vp]),
+        'ngb200_pipeline_create': (i32, [C.POINTER(PipelineDesc), C.POINTER(vp)]),
+        'ngb200_pipeline_destroy': (None, [vp]),
+        'ngb200_pipeline_get_info': (i32, [vp, C.POINTER(PipelineInfo)]),
+        'ngb200_pipeline_source': (C.c_char_p, [vp]),
+        'ngb200_pipeline_launch': (i32, [vp, C.POINTER(Operand), C.POINTER(i64), i64, i32, C.POINTER(C.c_double), vp]),
         'ngb200_host_alloc': (i32, [C.POINTER(vp), i64]),
         'ngb200_host_free': (i32, [vp]),
         'ngb200_fill_normal': (i32, [vp, i64, u64, u64, C.c_double, i32, vp]),
@@ -111,6 +142,92 @@ def _i32(seq):
     return (C.c_int32 * max(len(seq), 1))(*seq)
 
 
+BIND_GLOBAL, BIND_SHARED = 0, 1
+
+
+def _program_desc(dtype, flags, in_width, in_mode, out_width, out_mode, n_params, consts, instr, stores, vec, keep):
+    """ProgramDesc over ctypes arrays; the arrays are appended to `keep` (they must outlive the C call)."""
+    d = ProgramDesc()
+    d.dtype, d.flags = dtype, flags
+    d.n_inputs = len(in_width)
+    iw, im = _i32(in_width), _i32(in_mode)
+    d.input_width, d.input_mode = iw, im
+    d.n_outputs = len(out_width)
+    ow, om = _i32(out_width), _i32(out_mode)
+    d.output_width, d.output_mode = ow, om
+    d.n_params = n_params
+    cs = (C.c_double * max(len(consts), 1))(*consts)
+    d.n_consts, d.consts = len(consts), cs
+    ins = (Instr * max(len(instr), 1))(*[Instr(*map(int, t)) for t in instr])
+    d.n_instr, d.instr = len(instr), ins
+    sts = (Store * max(len(stores), 1))(*[Store(*map(int, t)) for t in stores])
+    d.n_stores, d.stores = len(stores), sts
+    d.vec = vec
+    keep.extend([iw, im, ow, om, cs, ins, sts])
+    return d
+
+
+class PipelineProgram:
+    """A compiled pipeline (include/numga_b200.h `ngb200_pipeline_*`): several straight-line programs in ONE kernel,
+    exchanging values through shared memory.  Built by numga_b200/pipeline.py."""
+
+    def __init__(self, dtype, flags, items_per_tile, globals_, shared, phases, loop, n_params, threads_per_tile=0):
+        """globals_: [(width, domain | -1, is_index)]; shared: [(width, domain)];
+        phases: [(ir dict, domain, [(kind, slot, index)] inputs, [(kind, slot, index)] outputs)]"""
+        keep = []
+        d = PipelineDesc()
+        d.dtype, d.flags = dtype, flags
+        ipt = _i32(items_per_tile)
+        d.n_domains, d.items_per_tile = len(items_per_tile), ipt
+        gw, gd, gi = _i32([g[0] for g in globals_]), _i32([g[1] for g in globals_]), _i32([int(g[2]) for g in globals_])
+        d.n_globals, d.global_width, d.global_domain, d.global_is_index = len(globals_), gw, gd, gi
+        sw, sd = _i32([s[0] for s in shared]), _i32([s[1] for s in shared])
+        d.n_shared, d.shared_width, d.shared_domain = len(shared), sw, sd
+        arr = (PhaseDesc * len(phases))()
+        for k, (ir, domain, ins, outs) in enumerate(phases):
+            arr[k].program = _program_desc(dtype, flags, ir['in_width'], [VARYING] * len(ir['in_width']), ir['out_width'],
+                                           [VARYING] * len(ir['out_width']), ir['n_params'], ir['consts'], ir['instr'],
+                                           ir['stores'], 0, keep)
+            arr[k].domain = domain
+            bi = (Bind * max(len(ins), 1))(*[Bind(*map(int, b)) for b in ins])
+            bo = (Bind * max(len(outs), 1))(*[Bind(*map(int, b)) for b in outs])
+            arr[k].inputs, arr[k].outputs = bi, bo
+            keep.extend([bi, bo])
+        d.n_phases, d.phases = len(phases), arr
+        d.loop_begin, d.loop_end = loop
+        d.n_params, d.threads_per_tile = n_params, threads_per_tile
+        h = C.c_void_p()
+        check(lib.ngb200_pipeline_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self.n_globals, self.n_domains, self.n_params = len(globals_), len(items_per_tile), n_params
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.ngb200_pipeline_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def source(self):
+        return lib.ngb200_pipeline_source(self.handle).decode()
+
+    @property
+    def info(self):
+        info = PipelineInfo()
+        check(lib.ngb200_pipeline_get_info(self.handle, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in PipelineInfo._fields_}
+
+    def launch(self, globals_, domain_items, n_tiles, repeat=1, params=(), stream=0):
+        """globals_: [(device_ptr, comp_stride, batch_stride)] per global operand (index arrays: (ptr, 0, 1))."""
+        assert len(globals_) == self.n_globals and len(domain_items) == self.n_domains
+        p = (C.c_double * max(len(params), 1))(*params)
+        n = (C.c_int64 * self.n_domains)(*[int(x) for x in domain_items])
+        check(lib.ngb200_pipeline_launch(self.handle, Program._operands(globals_), n, int(n_tiles), int(repeat), p,
+                                         C.c_void_p(stream)))
+
+
 class Program:
     """A compiled straight-line program (one cubin: a contiguous kernel, vectorised where that pays, + a generic
     strided / gather-scatter kernel)."""
@@ -125,22 +242,8 @@ class Program:
     @classmethod
     def from_ir(cls, dtype, flags, in_width, in_mode, out_width, out_mode, n_params, consts, instr, stores, vec=0):
         """instr: sequence of (op, a, b, c); stores: sequence of (operand, component, value)."""
-        d = ProgramDesc()
-        d.dtype, d.flags = dtype, flags
-        d.n_inputs = len(in_width)
-        iw, im = _i32(in_width), _i32(in_mode)
-        d.input_width, d.input_mode = iw, im
-        d.n_outputs = len(out_width)
-        ow, om = _i32(out_width), _i32(out_mode)
-        d.output_width, d.output_mode = ow, om
-        d.n_params = n_params
-        cs = (C.c_double * max(len(consts), 1))(*consts)
-        d.n_consts, d.consts = len(consts), cs
-        ins = (Instr * max(len(instr), 1))(*[Instr(*map(int, t)) for t in instr])
-        d.n_instr, d.instr = len(instr), ins
-        sts = (Store * max(len(stores), 1))(*[Store(*map(int, t)) for t in stores])
-        d.n_stores, d.stores = len(stores), sts
-        d.vec = vec
+        keep = []
+        d = _program_desc(dtype, flags, in_width, in_mode, out_width, out_mode, n_params, consts, instr, stores, vec, keep)
         h = C.c_void_p()
         check(lib.ngb200_program_create(C.byref(d), C.byref(h)))
         return cls(h.value, in_width, in_mode, out_width, out_mode, n_params, dtype)

@@ -69,11 +69,63 @@ def emulate_launches():
             return orig_op_call(self, *inputs)
         return self.context.engine.call(('operator', self.operator.uid), lambda *xs: orig_op_call(self, *xs), inputs)
 
-    B.CompiledFunction.launch, B.B200Operator.__call__ = compiled_call, operator_call
+    def pipeline_launch(self, arrays, items, repeat=1, params=()):
+        """Pipelines (numga_b200/pipeline.py): tiles are independent and phases are separated by barriers, so running
+        every phase over the WHOLE domain with shared buffers as full-size arrays is the same computation."""
+        pipe, ctx = self.pipe, self.context
+        np_dtype = B._NP_DTYPE[ctx.dtype]
+        counts = [int(items[d]) for d in pipe.domains]
+        G = []
+        for name, width, domain, is_index in pipe.globals:
+            a = arrays[name]
+            G.append(a if is_index else (a.flat if isinstance(a, B.B200DenseOperator) else a.values))
+        S = [np.zeros((counts[d], w), np_dtype) for w, d in pipe.shared]
+
+        def read(bind, n):
+            kind, slot, index = bind
+            src = S[slot] if kind == rt.BIND_SHARED else G[slot].detach().cpu().numpy()
+            if kind == rt.BIND_GLOBAL and pipe.globals[slot][2] < 0:
+                return src.reshape(-1)
+            src = src.reshape(-1, src.shape[-1])
+            return src[G[index].cpu().numpy()[:n]] if index >= 0 else src[:n]
+
+        def write(bind, n, values):
+            kind, slot, index = bind
+            if kind == rt.BIND_SHARED:
+                if index >= 0:
+                    S[slot][G[index].cpu().numpy()[:n]] = values
+                else:
+                    S[slot][:n] = values
+            else:
+                rows = torch.as_tensor(np.ascontiguousarray(values)).to(ctx.dtype)
+                if index >= 0:
+                    G[slot][G[index][:n]] = rows
+                else:
+                    G[slot][:n] = rows
+
+        def run(k):
+            ir, d, ins, outs = self.phases[k]
+            n = counts[d]
+            res = run_ir(ir, [read(b, n) for b in ins], np_dtype, [float(p) for p in params])
+            for b, o in zip(outs, res):
+                write(b, n, o[:n])
+        lo, hi = self.loop
+        for k in range(lo):
+            run(k)
+        for _ in range(repeat):
+            for k in range(lo, hi):
+                run(k)
+        for k in range(hi, len(self.phases)):
+            run(k)
+        return []
+
+    from numga_b200 import pipeline as PL
+    orig_pipe = PL.CompiledPipeline.launch
+    B.CompiledFunction.launch, B.B200Operator.__call__, PL.CompiledPipeline.launch = compiled_call, operator_call, pipeline_launch
     try:
         yield
     finally:
-        B.CompiledFunction.launch, B.B200Operator.__call__ = orig_call, orig_op_call
+        B.CompiledFunction.launch, B.B200Operator.__call__, PL.CompiledPipeline.launch = orig_call, orig_op_call, orig_pipe
 
 
 def emulated_context(algebra, dtype=torch.float64, mode='faithful'):

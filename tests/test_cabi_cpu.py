@@ -159,3 +159,31 @@ int main(void) {
     assert lines[1].split() == [str(x) for x in (ctypes.sizeof(d), d.consts.offset, d.stores.offset, d.vec.offset)]
     assert lines[2].split() == [str(ctypes.sizeof(rt.ProgramInfo)), str(rt.ProgramInfo.cubin_bytes.offset)]
     assert lines[3].split() == [str(x) for x in (rt.VARYING, rt.BROADCAST, rt.INDEXED, rt.REDUCED, rt.TILED)]
+
+
+def test_pipeline_c_abi_compiles_and_validates():
+    """ngb200_pipeline_*: two phases over two domains exchanging through a shared buffer compile into ONE sm_100a
+    kernel (barrier between the phases, gather through an index operand); malformed descriptions are refused."""
+    I, S = rt.BIND_GLOBAL, rt.BIND_SHARED
+    # phase 0 (domain 0, "nodes"): s = 2 * a                       -> shared buffer 0
+    # phase 1 (domain 1, "edges"): out = s[i0] - s[i1] (gathered)  -> global
+    scale = dict(in_width=[1], out_width=[1], n_params=0, consts=[2.0], stores=[(0, 0, 2)],
+                 instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_CONST, 0, 0, 0), (rt.OP_MUL, 0, 1, 0)])
+    diff = dict(in_width=[1, 1], out_width=[1], n_params=0, consts=[], stores=[(0, 0, 2)],
+                instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_INPUT, 1, 0, 0), (rt.OP_SUB, 0, 1, 0)])
+    globals_ = [(1, 0, False), (1, 1, True), (1, 1, True), (1, 1, False)]       # a, i0, i1, out
+    phases = [(scale, 0, [(I, 0, -1)], [(S, 0, -1)]), (diff, 1, [(S, 0, 1), (S, 0, 2)], [(I, 3, -1)])]
+    p = rt.PipelineProgram(rt.F32, rt.FAST, [64, 63], globals_, [(1, 0)], phases, (0, 0), 0)
+    src = p.source
+    assert src.count('__syncthreads()') == 2 and 'ngb_pipeline' in src and 'p.idx[0][gi] - tile * 64LL' in src
+    info = p.info
+    assert info['shared_bytes'] == 64 * 4 and info['threads_per_tile'] == 64 and info['n_instr'] >= 2
+    with pytest.raises(rt.NGB200Error, match='no CPU fallback|CUDA'):
+        p.launch([(1, 1, 1)] * 4, [64, 63], 1)
+    bad = [(scale, 0, [(I, 0, -1)], [(S, 0, -1)]), (diff, 1, [(S, 0, -1), (S, 0, 2)], [(I, 3, -1)])]
+    with pytest.raises(rt.NGB200Error, match='another domain'):
+        rt.PipelineProgram(rt.F32, rt.FAST, [64, 63], globals_, [(1, 0)], bad, (0, 0), 0)
+    with pytest.raises(rt.NGB200Error, match='loop'):
+        rt.PipelineProgram(rt.F32, rt.FAST, [64, 63], globals_, [(1, 0)], phases, (1, 3), 0)
+    with pytest.raises(rt.NGB200Error, match='shared memory'):
+        rt.PipelineProgram(rt.F32, rt.FAST, [1024, 63], globals_, [(60, 0)], phases, (0, 0), 0)

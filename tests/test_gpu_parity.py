@@ -422,3 +422,48 @@ def test_parity_batch_of_a_million_items_vs_oracle(name, log2n):
     got = _run(case, ctx, ins, 'jit').numpy()
     assert got.shape == want.shape
     assert _rel_err(got, want) < (CHAIN_TOL[np.float32] if 'roundtrip' in name else TOL[np.float32])
+
+
+def test_eager_fast_path_repeated_calls_layout_changes_and_scalars():
+    """The C++ fast path (csrc/fastcall.cpp + ngb200_plan_*) takes over from the second call with a layout: results
+    must equal the first (python-path) call bit for bit, be fresh tensors each time, follow layout changes, carry
+    scalar launch parameters, and work for broadcast operands and odd batch sizes (vector kernel + scalar tail)."""
+    from numga_b200 import fast
+    assert fast.module is not None, 'the fast-path extension was not built (numga_b200/_ngb200_fast.so)'
+    ctx = _ctx((3, 0, 1), np.float32)
+    rng = np.random.default_rng(5)
+    for n in (4099, 64, 1):
+        a = ctx.multivector.motor(rng.standard_normal((n, 8)).astype(np.float32))
+        b = ctx.multivector.motor(rng.standard_normal((n, 8)).astype(np.float32))
+        first = a * b
+        again = [a * b for _ in range(3)]
+        for r in again:
+            assert r.values.data_ptr() != first.values.data_ptr()
+            assert torch.equal(r.values, first.values)
+        oc = O.context((3, 0, 1), np.float32)
+        want = (oc.multivector('even_grade', a.numpy()) * oc.multivector('even_grade', b.numpy())).values
+        assert _rel_err(again[-1].numpy(), want) <= 1e-5
+    # broadcast motor, then the same function on another layout, then back
+    R = ctx.multivector.motor(rng.standard_normal(8).astype(np.float32))
+    p1 = ctx.multivector.antivector(rng.standard_normal((1000, 4)).astype(np.float32))
+    p2 = ctx.multivector.antivector(rng.standard_normal((10, 100, 4)).astype(np.float32))
+    f = ctx.jit(lambda r, x: r >> x)
+    w1, w2 = f(R, p1), f(R, p2)
+    for _ in range(2):
+        assert torch.equal(f(R, p1).values, w1.values) and torch.equal(f(R, p2).values, w2.values)
+    assert f(R, p2).shape == (10, 100)
+    # scalar launch parameters change between calls without recompiling
+    g = ctx.jit(lambda x, s: x * s + 1)
+    for s in (0.5, 2.0, 2.0, -3.0):
+        got = g(p1, s).numpy()
+        assert _rel_err(got[:, 1:], p1.numpy() * np.float32(s)) <= 1e-6 and got.shape == (1000, 5)
+    # a view with another stride of the same shape must NOT reuse the contiguous plan's addressing
+    big = ctx.multivector.motor(rng.standard_normal((20000, 8)).astype(np.float32))
+    half = big[::2]
+    assert half.values.stride(0) == 2
+    c = ctx.multivector.motor(rng.standard_normal((10000, 8)).astype(np.float32))
+    for _ in range(2):
+        c * c                                    # a contiguous plan is hot when the strided call arrives
+    want = (c * ctx.multivector.motor(half.numpy())).numpy()
+    for _ in range(3):
+        assert np.array_equal((c * half).numpy(), want)

@@ -66,6 +66,24 @@ def _fused_steps(bodies, sets, tag, steps=(1, 2, 5)):
     return b
 
 
+def _chain_steps(bodies, sets, tag, steps=(1, 2, 5)):
+    """The chain-resident single-kernel step (`ChainStep`): one sub-step per launch, then several per launch."""
+    from numga_b200.examples.physics import ChainStep
+    mt, rt_ = TOL[tag]
+    cs = ChainStep(bodies, sets, unroll=1)
+    b = bodies
+    for step in range(1, max(steps) + 1):
+        b = cs.integrate(b, DT)
+        if step in steps:
+            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt * step
+            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_ * step
+    for unroll in sorted(set(steps) - {1}):                      # `unroll` sub-steps inside ONE launch
+        b = ChainStep(bodies, sets, unroll=unroll).integrate(bodies, DT)
+        assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{unroll}/motor']) < mt * unroll
+        assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{unroll}/rate']) < rt_ * unroll
+    return b
+
+
 def _start(ctx, tag):
     from numga_b200.examples.physics import setup_bodies
     bodies, sets = setup_bodies(ctx, n_bodies=12)
@@ -96,6 +114,19 @@ def test_physics_generic_and_fused_step_cpu_emulated():
         assert np.array_equal(many.rate.values.numpy().reshape(3, 12, 6), np.broadcast_to(one.rate.values.numpy(), (3, 12, 6)))
         # the caller's state is never modified (immutable value semantics)
         assert _err(bodies.rate.values.numpy(), G['f64/start/rate']) == 0
+        # the chain-resident pipeline kernel: same traced bodies, one launch per step / per several steps
+        _chain_steps(bodies, sets, 'f64', steps=(1, 2))
+        from numga_b200.examples.physics import ChainStep
+        cs = ChainStep(big, bsets, unroll=2, bodies_per_tile=24)
+        assert (cs.block, cs.blocks_per_tile) == (12, 2)          # 3 chains, 2 per tile: the last tile is partial
+        many2 = cs.integrate(big, DT)
+        two = fs.integrate(one, DT)
+        assert np.array_equal(many2.motor.values.numpy().reshape(3, 12, 8), np.broadcast_to(two.motor.values.numpy(), (3, 12, 8)))
+        assert np.array_equal(many2.rate.values.numpy().reshape(3, 12, 6), np.broadcast_to(two.rate.values.numpy(), (3, 12, 6)))
+        assert _err(big.rate.values.numpy().reshape(3, 12, 6)[0], G['f64/start/rate']) == 0
+        with pytest.raises(ValueError):                           # a system without block structure is refused
+            from numga_b200.examples.physics import _block_structure
+            _block_structure(12, [torch.tensor([[0, 5], [11, 6]])], max_block=6)
 
 
 # ---- GPU tier ----------------------------------------------------------------------------------------------------------
@@ -108,6 +139,7 @@ def test_physics_step_gpu_vs_reference(tag, mode):
     bodies, sets = _start(ctx, tag)
     _stages(bodies, sets, tag)
     _fused_steps(bodies, sets, tag)
+    _chain_steps(bodies, sets, tag)
 
 
 @pytest.mark.gpu
@@ -129,6 +161,15 @@ def test_physics_replicated_chains_gpu():
     assert np.array_equal(m, np.broadcast_to(one.motor.values.cpu().numpy(), m.shape))
     assert np.array_equal(r, np.broadcast_to(one.rate.values.cpu().numpy(), r.shape))
     assert np.isfinite(many.kinetic_energy().values.cpu().numpy()).all()
+    # the chain-resident kernel on the same batch (1000 chains = 100 tiles of 10 chains; with 7 chains per tile the last
+    # tile is partial): three sub-steps in one launch give the three-launch state of the six-kernel arrangement
+    from numga_b200.examples.physics import ChainStep
+    for bpt in (128, 84):
+        got = ChainStep(big, bsets, unroll=3, bodies_per_tile=bpt).integrate(big, DT)
+        assert _err(got.motor.values.cpu().numpy(), many.motor.values.cpu().numpy()) < 1e-5
+        assert _err(got.rate.values.cpu().numpy(), many.rate.values.cpu().numpy()) < 5e-3
+        gm = got.motor.values.cpu().numpy().reshape(n_chains, 12, 8)
+        assert np.array_equal(gm, np.broadcast_to(gm[0], gm.shape))          # every chain follows the same arithmetic
 
 
 # ---- free tumbling (numga/examples/tennis_racket_theorem.py) ------------------------------------------------------------
