@@ -332,9 +332,13 @@ class ChainStep:
         n_bodies = bodies.motor.shape[0]
         block, per_block = _block_structure(n_bodies, [c.body_idx for c in self.sets])
         if bodies_per_tile is None:
-            bodies_per_tile = 128 if ctx.dtype == torch.float32 else 64
+            bodies_per_tile = 384 if ctx.dtype == torch.float32 else 192      # measured on B200 (profiles/r02_chain_sweep.txt)
         k = max(1, bodies_per_tile // block)                       # whole blocks (chains) per tile
         self.block, self.blocks_per_tile = block, k
+        if not threads_per_tile:
+            # one thread per constraint in the constraint phases (every warp busy there: they are 60 % of the work), two
+            # bodies per thread in the body phases: 8.07 vs 6.60 G body-steps/s against one thread per body
+            threads_per_tile = min(1024, -(-max([c * k for c in per_block] + [-(-block * k // 2)]) // 32) * 32)
         S = ctx.subspace
         names = ['body'] + [f'set{j}' for j in range(len(self.sets))]
         pipe = Pipeline(ctx, dict(zip(names, [block * k] + [c * k for c in per_block])), threads_per_tile=threads_per_tile)
