@@ -1722,6 +1722,40 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             }
         appendf(s, "%s    }\n%s  }\n%s}\n%s__syncthreads();\n", ind, ind, ind, ind);
     };
+    // L2 prefetch of what the LATER phases of this tile read from global memory (per-item constants and tables that are
+    // not parked in shared memory): issued before the first phase, so that their DRAM latency overlaps the load phase
+    // and the first compute phases instead of being exposed at the head of every later phase.
+    if (env_int("NGB200_PIPE_PREFETCH", 0)) {     // measured on B200: 5.41 vs 5.77 G body-steps/s with it on (profiles/r02_chain_sweep.txt): off
+        std::map<std::pair<int, int>, int> seen;        // (global slot, component) -> domain
+        for (size_t k = 1; k < Q.phases.size(); ++k) {
+            PipePhase &ph = Q.phases[k];
+            Gen &g = *gens[k];
+            std::vector<char> used(g.NX > 0 ? g.NX : 1, 0);
+            for (size_t v = 0; v < ph.prog->instr.size(); ++v) {
+                const ngb200_instr &I = ph.prog->instr[v];
+                if (I.op == NGB200_OP_INPUT && g.live[v] && !g.uniform[v]) used[g.xoff[I.a] + I.b] = 1;
+            }
+            for (size_t j = 0; j < ph.in.size(); ++j) {
+                const ngb200_bind &b = ph.in[j];
+                if (b.kind != NGB200_BIND_GLOBAL || b.index >= 0 || ph.prog->in_mode[j] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < ph.prog->in_width[j]; ++c)
+                    if (used[g.xoff[j] + c]) seen[std::make_pair(b.slot, c)] = ph.domain;
+            }
+        }
+        std::map<int, std::vector<std::pair<int, int>>> by_domain;
+        for (auto &kv : seen) by_domain[kv.second].push_back(kv.first);
+        for (auto &kv : by_domain) {
+            const int d = kv.first, ipt = Q.ipt[d];
+            // one prefetch per 32-byte sector: every 8th (fp32) / 4th (fp64) item of a row issues it
+            const int per = 32 / es;
+            appendf(s, "    for (int i = threadIdx.x * %d; i < %d; i += NGB_TPB * %d) {\n", per, ipt, per);
+            appendf(s, "      const long long gi = tile * %dLL + i;\n      if (gi < p.n[%d]) {\n", ipt, d);
+            for (auto &sc : kv.second)
+                appendf(s, "        asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p.g[%d].ptr + %dLL * p.g[%d].cs + gi));\n",
+                        Q.gslot[sc.first], sc.second, Q.gslot[sc.first]);
+            s += "      }\n    }\n";
+        }
+    }
     for (int k = 0; k < Q.loop_begin; ++k) emit_phase(k, "    ");
     if (Q.loop_end > Q.loop_begin) {
         s += "    for (int rep = 0; rep < p.repeat; ++rep) {\n";

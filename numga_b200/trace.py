@@ -586,14 +586,13 @@ def build_vjp(ir, np_dtype, faithful=False, wanted=None):
     for k, c, v in ir['stores']:
         acc(new[v], cot_regs[k][c])
     zero, half = t.const(0.0), t.const(0.5)
-    # adjoints are keyed by NEW ids (hash-consing can merge old values); walk old instructions backwards, visiting
-    # every new id once, at its last defining old instruction
-    seen = set()
-    for old in range(len(ir['instr']) - 1, -1, -1):
-        v = new[old]
-        if v in seen or v not in adj:
+    # Adjoints are keyed by NEW ids (hash-consing and the simplifier can merge several old values into one).  Operands
+    # always have smaller ids than their consumers, so descending id order is a reverse topological order: every
+    # consumer of v has contributed to adj[v] before v is expanded, whatever the old instruction order was.
+    n_forward = len(t.instr)
+    for v in range(n_forward - 1, -1, -1):
+        if v not in adj:
             continue
-        seen.add(v)
         op, a, b, c = t.instr[v]
         g = adj[v]
         if op in (rt.OP_INPUT, rt.OP_CONST, rt.OP_PARAM):
@@ -616,7 +615,8 @@ def build_vjp(ir, np_dtype, faithful=False, wanted=None):
         elif op == rt.OP_RCP:
             acc(a, t.neg(t.mul(g, t.mul(v, v))))
         elif op == rt.OP_ABS:
-            acc(a, t._emit(rt.OP_SELECT_GT0, a, g, t.neg(g)))
+            # d|x|/dx = sign(x), and 0 at x == 0 (torch's convention): g if x > 0, else (-g if -x > 0 else 0)
+            acc(a, t._emit(rt.OP_SELECT_GT0, a, g, t._emit(rt.OP_SELECT_GT0, t.neg(a), t.neg(g), zero)))
         elif op == rt.OP_NAN_TO_NUM:
             acc(a, g)
         elif op == rt.OP_FMA:

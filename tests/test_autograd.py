@@ -131,3 +131,68 @@ def test_broadcast_operand_gradient_is_reduced_inside_the_kernel(where):
         want = Rn.grad.sum(dim=0)
         assert tuple(R.grad.shape) == (8,)
         assert float((R.grad - want).abs().max() / want.abs().max()) < 1e-10
+
+
+def test_vjp_of_ir_with_duplicate_values_and_abs_at_zero():
+    """Regressions (round-1 ADVICE): (1) forward IR that is NOT hash-consed -- two identical instructions that the
+    replay merges into one value -- must keep every consumer's adjoint contribution (the reverse sweep runs over the
+    new ids in descending order); (2) d|x|/dx at x == 0 is 0, as in torch, not -1."""
+    from ir_interp import run_ir
+    from numga_b200 import runtime as rt
+    from numga_b200.trace import build_vjp
+    ir = dict(in_width=[1, 1], in_mode=[rt.VARYING, rt.VARYING], out_width=[1], n_params=0, consts=[],
+              instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_INPUT, 1, 0, 0), (rt.OP_MUL, 0, 1, 0), (rt.OP_SQRT, 2, 0, 0),
+                     (rt.OP_MUL, 0, 1, 0), (rt.OP_ADD, 3, 4, 0)],          # sqrt(a*b) + a*b, the product stated twice
+              stores=[(0, 0, 5)])
+    vjp = build_vjp(ir, np.float64)
+    a, b, g = np.array([[1.5], [0.25]]), np.array([[2.0], [4.0]]), np.array([[1.0], [3.0]])
+    ga, gb = run_ir(vjp, [a, b, g], np.float64)
+    want = g * (0.5 / np.sqrt(a * b) + 1.0)
+    assert np.allclose(ga, want * b, rtol=1e-14) and np.allclose(gb, want * a, rtol=1e-14)
+    ir_abs = dict(in_width=[1], in_mode=[rt.VARYING], out_width=[1], n_params=0, consts=[],
+                  instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_ABS, 0, 0, 0)], stores=[(0, 0, 1)])
+    x, g = np.array([[-2.0], [0.0], [3.0]]), np.array([[5.0], [5.0], [5.0]])
+    (gx,) = run_ir(build_vjp(ir_abs, np.float64), [x, g], np.float64)
+    assert gx.reshape(-1).tolist() == [-5.0, 0.0, 5.0]
+    t = torch.tensor(x.reshape(-1), requires_grad=True)
+    t.abs().backward(torch.tensor(g.reshape(-1)))
+    assert t.grad.tolist() == gx.reshape(-1).tolist()
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_torch_compile_fullgraph_motor_fitting(where):
+    """`ctx.torch_op`: generated programs registered as `torch.library.custom_op`s (fake kernels from the IR's output
+    layout, backward = the VJP program) survive `torch.compile(fullgraph=True)`: the motor-fitting loop of
+    `test_gradient_descent_recovers_a_motor`, with loss AND gradient computed by ONE compiled graph."""
+    rng = np.random.default_rng(3)
+    with _context((3, 0, 1), where) as ctx:
+        S = ctx.subspace
+        target = ctx.multivector.bivector(0.3 * rng.standard_normal(6)).exp()
+        p = ctx.multivector.antivector(np.concatenate([rng.standard_normal((32, 3)), np.ones((32, 1))], axis=1))
+        q = (target >> p).values.detach()
+        spin = ctx.torch_op(lambda b, x: b.exp() >> x, S.bivector(), S.antivector())
+
+        def loss_fn(b, x, y):
+            return ((spin(b, x) - y) ** 2).sum()
+        # eager custom op: same value and gradient as the autograd.Function path
+        b0 = torch.tensor(0.1 * rng.standard_normal(6), dtype=torch.float64, device=ctx.device, requires_grad=True)
+        l_op = loss_fn(b0, p.values, q)
+        (g_op,) = torch.autograd.grad(l_op, b0)
+        m = ctx.multivector(values=b0, subspace=S.bivector()).exp()
+        l_ref = (((m >> p).values - q) ** 2).sum()
+        (g_ref,) = torch.autograd.grad(l_ref, b0)
+        assert abs(l_op.item() - l_ref.item()) < 1e-12 * max(1, abs(l_ref.item()))
+        assert float((g_op - g_ref).abs().max()) < 1e-10 * float(g_ref.abs().max())
+        # compiled: fullgraph=True fails on any graph break (unsupported python, missing fake kernel ...)
+        compiled = torch.compile(loss_fn, fullgraph=True, backend='inductor' if where == 'gpu' else 'aot_eager')
+        b = torch.zeros(6, dtype=torch.float64, device=ctx.device, requires_grad=True)
+        opt = torch.optim.Adam([b], lr=0.05)
+        first = None
+        for _ in range(60 if where == 'gpu' else 25):
+            opt.zero_grad()
+            loss = compiled(b, p.values, q)
+            loss.backward()
+            opt.step()
+            first = loss.item() if first is None else first
+        assert loss.item() < 0.05 * first
+        torch.library.opcheck(spin.forward, ([b0.detach(), p.values],), test_utils=('test_schema', 'test_faketensor'))

@@ -111,3 +111,36 @@ def test_jitted_functions_inline_into_each_other():
     n = len(ctx.engine.cache)
     outer(ctx.multivector.motor(torch.zeros(4, 8)), ctx.multivector.antivector(torch.zeros(4, 4)))
     assert len(ctx.engine.cache) == n + 1            # one kernel for the whole thing, none for `inner` alone
+
+
+def test_batch_axis_sums_and_row_gathers_are_generated_kernels():
+    """`sum` / `mean` over a batch axis and `mv[index_array]` (numga/backend/numpy/multivector.py:30-56) run as generated
+    kernels: slices added in registers, a batch-reduced output for the only batch axis, rows gathered straight into
+    structure-of-arrays layout.  Semantics = numpy's on the values array (negative axes count the component axis)."""
+    from cpu_emulation import emulate_launches, emulated_context
+    rng = np.random.default_rng(3)
+    with emulate_launches():
+        ctx = emulated_context((3, 0, 1), torch.float64)
+        x = rng.standard_normal((5, 7, 4))
+        p = ctx.multivector.antivector(x)
+        n0 = len(ctx.engine.cache)
+        for axis in (0, 1, -2, -3):
+            assert np.allclose(p.sum(axis).numpy(), x.sum(axis), rtol=0, atol=1e-14), axis
+            assert np.allclose(p.mean(axis).numpy(), x.mean(axis), rtol=0, atol=1e-14), axis
+            assert p.sum(axis).subspace is p.subspace and p.sum(axis).shape == x.sum(axis).shape[:-1]
+        assert any(k[0][0] == 'sum_slices' for k in ctx.engine.cache) and len(ctx.engine.cache) > n0
+        flat = ctx.multivector.antivector(x.reshape(35, 4))
+        assert np.allclose(flat.sum(0).numpy(), x.reshape(35, 4).sum(0), rtol=0, atol=1e-14) and flat.sum(0).shape == ()
+        assert np.allclose(flat.mean(-2).numpy(), x.reshape(35, 4).mean(0), rtol=0, atol=1e-14)
+        assert any(k[0][0] == 'reduce' for k in ctx.engine.cache)
+        with pytest.raises(AssertionError):
+            p.sum(-1)
+        big = ctx.multivector.antivector(rng.standard_normal((200, 3, 4)))         # more than 64 slices: folded
+        assert np.allclose(big.sum(0).numpy(), big.numpy().sum(0), rtol=0, atol=1e-13)
+        # row gathers: numpy index arrays, torch index tensors, negative and repeated indices, 2-D index arrays
+        idx = np.array([3, 0, 34, -1, 3])
+        got = flat[idx]
+        assert np.array_equal(got.numpy(), x.reshape(35, 4)[idx]) and got.values.stride(0) == 1
+        idx2 = torch.tensor([[0, 1, 2], [-3, 33, 5]])
+        assert np.array_equal(flat[idx2].numpy(), x.reshape(35, 4)[idx2.numpy()]) and flat[idx2].shape == (2, 3)
+        assert any(k[0] == ('gather',) for k in ctx.engine.cache)

@@ -16,10 +16,7 @@ from ir_interp import run_ir
 from numga_b200.backend import B200Context
 
 TORCH = {np.float32: torch.float32, np.float64: torch.float64}
-# exp/log chains amplify rounding differences: gate them against the oracle's own fp32 error level
-CHAIN_TOL = {np.float32: 2e-3, np.float64: 1e-10}
-TOL = {np.float32: 1e-5, np.float64: 1e-12}
-ILL_CONDITIONED = ('exp', 'log', 'roundtrip', 'motor_sqrt')
+from tolerances import gate         # derivation: profiles/r02_tolerances.md
 # Two things numpy does that no fixed evaluation order reproduces bit for bit (hard part 1):
 #  * einsum(optimize=True) pre-contracts a BROADCAST operand with the kernel in its own order;
 #  * `x ** -0.5` (roots.py:38-39, reached by `normalized` of objects whose x~x is a scalar) is libm pow,
@@ -47,7 +44,7 @@ def test_faithful_program_bit_exact(case, dtype):
     want = np.broadcast_to(want, got.shape)
     if case[0] in NOT_BIT_REPRODUCIBLE:
         err = np.abs(got - want).max(axis=-1) / np.abs(want).max(axis=-1)
-        assert err.max() < (CHAIN_TOL[dtype] if any(t in case[0] for t in ILL_CONDITIONED) else TOL[dtype])
+        assert err.max() < gate(case[0], dtype)
     else:
         assert np.array_equal(got, want, equal_nan=True), np.nanmax(np.abs(got - want))
 
@@ -61,7 +58,7 @@ def test_fast_program_within_tolerance(case, dtype):
     want = np.broadcast_to(want, got.shape)
     scale = np.maximum(np.abs(want).max(axis=-1), 1e-30)
     err = np.nan_to_num(np.abs(got - want).max(axis=-1) / scale)
-    tol = CHAIN_TOL[dtype] if any(t in case[0] for t in ILL_CONDITIONED) else TOL[dtype]
+    tol = gate(case[0], dtype)
     assert err.max() < tol, err.max()
 
 
