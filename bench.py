@@ -383,9 +383,10 @@ def rel_err(got, want):
 
 
 PARITY_N = 1 << 16
-# value gates of the benchmarked (fast) mode; derivation in profiles/r02_tolerances.md
-TOL = {'cfg1': 1e-5, 'cfg2': 1e-5, 'cfg4': 1e-5, 'cfg3_f32': 1e-3, 'cfg3_f64': 1e-10,
-       'cfg5_f32': (1e-5, 5e-3), 'cfg5_f64': (1e-12, 1e-10)}
+# value gates of the benchmarked (fast) mode against the reference at the same precision; derivation in
+# profiles/r02_tolerances.md (config 5: (motor, rate) after ONE sub-step; scaled per sub-step count below)
+TOL = {'cfg1': 1e-5, 'cfg2': 1e-5, 'cfg4': 1e-5, 'cfg3_f32': 2e-5, 'cfg3_f64': 2e-11,
+       'cfg5_f32': (1e-5, 0.8e-3), 'cfg5_f64': (1e-12, 1e-11)}
 
 
 def entry(cfg, name, n, ms, bytes_per_item, peak, unit='products/s', **extra):
@@ -421,6 +422,17 @@ def run_cfg1(torch, B200Context, rank, peak, faithful=True):
                 a * b
             host_us = (time.perf_counter() - t0) / reps * 1e6      # launches queue up: this is issue cost when < kernel time
             torch.cuda.synchronize()
+            # the same call on a 4096-item batch (kernel ~2 us): the GPU never limits, so this is the HOST cost of one
+            # eager operator application (python dispatch + result allocation + plan launch in csrc/fastcall.cpp)
+            sa, sb = device_mv(pga, S.even_grade(), 4096, 21, rank), device_mv(pga, S.even_grade(), 4096, 22, rank)
+            for _ in range(10):
+                sa * sb
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                sa * sb
+            host_small_us = (time.perf_counter() - t0) / reps * 1e6
+            torch.cuda.synchronize()
 
             def twenty(a, b):
                 for _ in range(20):
@@ -428,7 +440,7 @@ def run_cfg1(torch, B200Context, rank, peak, faithful=True):
                 return o
             g = pga.capture(twenty, a, b)
             ms_graph = time_steps(g.replay, 10, 3) / 20
-            extra = {'eager_call_us_wall': host_us, 'ms_in_cuda_graph': ms_graph,
+            extra = {'eager_call_us_wall': host_us, 'host_us_per_eager_call': host_small_us, 'ms_in_cuda_graph': ms_graph,
                      'frac_in_cuda_graph': 96 * n / ms_graph / 1e6 / peak,
                      'l2_note': '96 MB working set fits the 126 MB L2: fractions above 1.0 of the HBM copy peak are L2 hits'}
         if faithful:
@@ -458,8 +470,8 @@ def run_cfg3(torch, B200Context, rank, peak, faithful=True):
             want64 = O.context((3, 0, 1), np.float64).multivector('bivector', hb).exp().normalized().motor_log().values
             want = O.context((3, 0, 1), npd).multivector('bivector', hb.astype(npd)).exp().normalized().motor_log().values
         got = f(c.multivector.bivector(hb.astype(npd))).numpy()
-        # the chain amplifies rounding: the gate is the reference's own error at this precision against the fp64 result
-        e_gpu, e_ref = rel_err(got, want64), rel_err(want, want64)
+        # gated against the reference at the SAME precision; the errors against the fp64 result are reported next to it
+        e_gpu, e_ref, e_vs_ref = rel_err(got, want64), rel_err(want, want64), rel_err(got, want)
         tol = TOL['cfg3_' + tag]
         n = 1 << 28
         bv = device_mv(c, c.subspace.bivector(), n, 13, rank, scale=0.5)
@@ -474,7 +486,7 @@ def run_cfg3(torch, B200Context, rank, peak, faithful=True):
             extra['faithful_bit_exact_vs_oracle'] = bool(np.array_equal(ff(fc.multivector.bivector(hb.astype(npd))).numpy(), want))
         e = entry('cfg3_' + tag, f'config 3: exp->normalized->motor_log round trip, {tag}, batch 2^28, one fused kernel', n, ms, ub, peak,
                   flops_per_item=prog.info['n_instr'], tflops=prog.info['n_instr'] * n / ms / 1e9,
-                  parity_ok=bool(e_gpu <= max(tol, 2 * e_ref)), parity_err_vs_fp64=e_gpu, reference_err_vs_fp64=e_ref,
+                  parity_ok=bool(e_vs_ref <= tol), parity_err=e_vs_ref, parity_err_vs_fp64=e_gpu, reference_err_vs_fp64=e_ref,
                   parity_tol=tol, **extra)
         e['roofline']['bound'] = 'fp32 issue' if tag == 'f32' else 'fp64 pipe'
         e['roofline']['compute_bound'] = True

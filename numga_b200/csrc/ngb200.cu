@@ -1607,7 +1607,14 @@ struct ngb200_pipeline {
     int tpb = 128, minb = 1;
     int n_value_globals = 0, n_index_globals = 0;
     size_t smem = 0, param_bytes = 0;
-    std::vector<size_t> soff;                 // element offset of every shared buffer
+    std::vector<size_t> soff;                 // element offset of every shared buffer (component-major layout)
+    // record layout (NGB200_PIPE_RECORDS, default): all shared buffers of one domain form ONE record per item, accessed
+    // with 128-bit shared loads / stores; records are padded to an ODD number of 16-byte chunks plus one chunk every 8
+    // rows, which makes unit-stride AND stride-2 row accesses (the two bodies of neighbouring constraints) bank-conflict free
+    bool records = true;
+    std::vector<size_t> rec_off;              // element offset of every shared buffer inside its domain's record
+    std::vector<size_t> dom_base;             // element offset of every domain's record array
+    std::vector<int> dom_chunks;              // 16-byte chunks per record, per domain
     std::string source, hash;
     std::vector<char> cubin;
     bool cache_hit = false;
@@ -1704,8 +1711,36 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             const ngb200_instr &I = ph.prog->instr[v];
             if (I.op == NGB200_OP_INPUT && g.live[v] && !g.uniform[v]) used[g.xoff[I.a] + I.b] = 1;
         }
+        const int VW = f64 ? 2 : 4;                         // elements per 16-byte chunk
+        const char *VTn = f64 ? "double2" : "float4";
+        static const char *lane4[4] = {"x", "y", "z", "w"};
+        // element offset of (row r) of shared buffer `slot` in the record layout
+        auto record_base = [&](const ngb200_bind &b) -> std::string {
+            const int dd = Q.sdomain[b.slot];
+            std::string r = b.index >= 0 ? row_of(b) : std::string("i");
+            char buf[256];
+            snprintf(buf, sizeof buf, "sm + %zu + (%s * %d + (%s >> 3)) * %d + %zu", Q.dom_base[dd], r.c_str(), Q.dom_chunks[dd],
+                     r.c_str(), VW, Q.rec_off[b.slot]);
+            return buf;
+        };
         for (size_t j = 0; j < ph.in.size(); ++j) {
             if (ph.prog->in_mode[j] == NGB200_BROADCAST) continue;
+            if (Q.records && ph.in[j].kind == NGB200_BIND_SHARED) {
+                const int w = ph.prog->in_width[j];
+                std::string base = record_base(ph.in[j]);
+                appendf(s, "%s      { const T* rp = %s;\n", ind, base.c_str());
+                for (int c0 = 0; c0 < w; c0 += VW) {
+                    bool any = false;
+                    for (int c = c0; c < std::min(w, c0 + VW); ++c) any = any || used[g.xoff[j] + c];
+                    if (!any) continue;
+                    appendf(s, "%s        { const %s t = *reinterpret_cast<const %s*>(rp + %d);", ind, VTn, VTn, c0);
+                    for (int c = c0; c < std::min(w, c0 + VW); ++c)
+                        if (used[g.xoff[j] + c]) appendf(s, " x[%d] = t.%s;", g.xoff[j] + c, lane4[c - c0]);
+                    s += " }\n";
+                }
+                appendf(s, "%s      }\n", ind);
+                continue;
+            }
             for (int c = 0; c < ph.prog->in_width[j]; ++c) {
                 if (!used[g.xoff[j] + c]) continue;          // structurally dead component: never loaded
                 std::string a = address(ph.in[j], c);
@@ -1714,12 +1749,28 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             }
         }
         appendf(s, "%s      ngb_body_%zu(x, u%zu, y);\n", ind, k, k);
-        for (size_t j = 0; j < ph.out.size(); ++j)
+        for (size_t j = 0; j < ph.out.size(); ++j) {
+            if (Q.records && ph.out[j].kind == NGB200_BIND_SHARED) {
+                const int w = ph.prog->out_width[j];
+                std::string base = record_base(ph.out[j]);
+                appendf(s, "%s      { T* rp = %s;\n", ind, base.c_str());
+                for (int c0 = 0; c0 < w; c0 += VW) {           // (the padding lanes of the last chunk belong to this buffer)
+                    appendf(s, "%s        { %s t;", ind, VTn);
+                    for (int l = 0; l < VW; ++l) {
+                        if (c0 + l < w) appendf(s, " t.%s = y[%d];", lane4[l], g.yoff[j] + c0 + l);
+                        else appendf(s, " t.%s = T(0);", lane4[l]);
+                    }
+                    appendf(s, " *reinterpret_cast<%s*>(rp + %d) = t; }\n", VTn, c0);
+                }
+                appendf(s, "%s      }\n", ind);
+                continue;
+            }
             for (int c = 0; c < ph.prog->out_width[j]; ++c) {
                 std::string a = address(ph.out[j], c);
                 if (ph.out[j].kind == NGB200_BIND_SHARED) appendf(s, "%s      *(%s) = y[%d];\n", ind, a.c_str(), g.yoff[j] + c);
                 else appendf(s, "%s      NGB_ST(%s, y[%d]);\n", ind, a.c_str(), g.yoff[j] + c);
             }
+        }
         appendf(s, "%s    }\n%s  }\n%s}\n%s__syncthreads();\n", ind, ind, ind, ind);
     };
     // L2 prefetch of what the LATER phases of this tile read from global memory (per-item constants and tables that are
@@ -1802,6 +1853,25 @@ extern "C" int ngb200_pipeline_create(const ngb200_pipeline_desc *d, ngb200_pipe
         off += (size_t)Q->swidth[k] * Q->ipt[Q->sdomain[k]];
     }
     Q->smem = off * es;
+    Q->records = env_int("NGB200_PIPE_RECORDS", 1) != 0;
+    if (Q->records) {
+        const int VW = 16 / es;
+        Q->rec_off.assign(d->n_shared, 0);
+        Q->dom_base.assign(d->n_domains, 0);
+        Q->dom_chunks.assign(d->n_domains, 0);
+        size_t total = 0;
+        for (int dd = 0; dd < d->n_domains; ++dd) {
+            size_t rec = 0;
+            for (int k = 0; k < d->n_shared; ++k)
+                if (Q->sdomain[k] == dd) { Q->rec_off[k] = rec; rec += (size_t)(Q->swidth[k] + VW - 1) / VW * VW; }
+            int chunks = (int)(rec / VW);
+            if (chunks && chunks % 2 == 0) chunks += 1;                      // odd number of 16-byte chunks per record
+            Q->dom_chunks[dd] = chunks;
+            Q->dom_base[dd] = total;
+            if (chunks) total += ((size_t)Q->ipt[dd] * chunks + (Q->ipt[dd] >> 3) + 1) * VW;
+        }
+        Q->smem = total * es;
+    }
     if (Q->smem > 227 * 1024) return fail(NGB200_ERR_INVALID, "tile needs %zu bytes of shared memory (limit 232448)", Q->smem);
     Q->tpb = d->threads_per_tile > 0 ? d->threads_per_tile : std::min(256, (max_ipt + 31) / 32 * 32);
     if (Q->tpb % 32 || Q->tpb > 1024) return fail(NGB200_ERR_INVALID, "threads per tile must be a multiple of 32, at most 1024");

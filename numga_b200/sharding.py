@@ -23,6 +23,26 @@ def shard_multivector(mv, world_size, rank):
     return mv[start:stop]
 
 
+def shard_chains(bodies, constraint_sets, world_size, rank, bodies_per_chain=None):
+    """This rank's share of a block-structured rigid-body system (config 5): whole chains only, so constraints never
+    cross ranks and the step needs no exchange.  Body indices of the constraint sets are rebased to the
+    local slice.  Returns (bodies, constraint_sets) of the same classes."""
+    from numga_b200.examples.physics import Body, Constraint, _block_structure
+    n = bodies.motor.shape[0]
+    if bodies_per_chain is None:
+        bodies_per_chain, _ = _block_structure(n, [c.body_idx for c in constraint_sets])
+    n_chains = n // bodies_per_chain
+    c0, c1 = shard_bounds(n_chains, world_size, rank, align=1)
+    b0, b1 = c0 * bodies_per_chain, c1 * bodies_per_chain
+    local = Body(*(getattr(bodies, f)[b0:b1] for f in Body._FIELDS))
+    sets = []
+    for c in constraint_sets:
+        per_chain = c.body_idx.shape[1] // n_chains
+        k0, k1 = c0 * per_chain, c1 * per_chain
+        sets.append(Constraint(c.body_idx[:, k0:k1] - b0, c.anchors[:, k0:k1], c.compliance[k0:k1]))
+    return local, sets
+
+
 def gather_values(values, dist, total_items=None):
     """OPTIONAL final gather of per-rank SoA value slices [n_local, k] -> [sum n_local, k] on every rank
     (NCCL all_gather over NVLink on GPUs, gloo on CPU in tests).  Not part of the hot path."""

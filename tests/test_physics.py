@@ -15,8 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 G = np.load(os.path.join(HERE, 'golden', 'physics.npz'))
 DT = 1 / 200
 TORCH = {'f32': torch.float32, 'f64': torch.float64}
-# position-like state (motors) / velocity-like state (rates: finite differences divided by dt amplify rounding by 1/dt)
-TOL = {'f64': (1e-12, 1e-10), 'f32': (1e-5, 5e-3)}
+# position-like state (motors) / velocity-like state (rates: finite differences divided by dt amplify rounding by 1/dt).
+# Gates after k sub-steps come from tolerances.physics_gate (derived in profiles/r02_tolerances.md: fp32 rates 1.2e-3 /
+# 1.6e-3 / 3e-3 after 1 / 2 / 5 sub-steps = 2x the measured kernel-vs-reference difference; the reference's own fp32
+# rates are 5.5e-4 .. 8.4e-4 away from its fp64 result)
+from tolerances import physics_gate
+TOL = {'f64': physics_gate('f64', 1), 'f32': physics_gate('f32', 1)}
 
 
 def _err(got, want):
@@ -61,8 +65,9 @@ def _fused_steps(bodies, sets, tag, steps=(1, 2, 5)):
     for step in range(1, max(steps) + 1):
         b = fs.integrate(b, DT)
         if step in steps:
-            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt * step
-            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_ * step
+            mt, rt_ = physics_gate(tag, step)
+            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt
+            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_
     return b
 
 
@@ -75,12 +80,14 @@ def _chain_steps(bodies, sets, tag, steps=(1, 2, 5)):
     for step in range(1, max(steps) + 1):
         b = cs.integrate(b, DT)
         if step in steps:
-            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt * step
-            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_ * step
+            mt, rt_ = physics_gate(tag, step)
+            assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{step}/motor']) < mt
+            assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{step}/rate']) < rt_
     for unroll in sorted(set(steps) - {1}):                      # `unroll` sub-steps inside ONE launch
         b = ChainStep(bodies, sets, unroll=unroll).integrate(bodies, DT)
-        assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{unroll}/motor']) < mt * unroll
-        assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{unroll}/rate']) < rt_ * unroll
+        mt, rt_ = physics_gate(tag, unroll)
+        assert _err(b.motor.values.cpu().numpy(), G[f'{tag}/step{unroll}/motor']) < mt
+        assert _err(b.rate.values.cpu().numpy(), G[f'{tag}/step{unroll}/rate']) < rt_
     return b
 
 
@@ -166,8 +173,8 @@ def test_physics_replicated_chains_gpu():
     from numga_b200.examples.physics import ChainStep
     for bpt in (128, 84):
         got = ChainStep(big, bsets, unroll=3, bodies_per_tile=bpt).integrate(big, DT)
-        assert _err(got.motor.values.cpu().numpy(), many.motor.values.cpu().numpy()) < 1e-5
-        assert _err(got.rate.values.cpu().numpy(), many.rate.values.cpu().numpy()) < 5e-3
+        assert np.array_equal(got.motor.values.cpu().numpy(), many.motor.values.cpu().numpy())     # same traced bodies,
+        assert np.array_equal(got.rate.values.cpu().numpy(), many.rate.values.cpu().numpy())       # same arithmetic
         gm = got.motor.values.cpu().numpy().reshape(n_chains, 12, 8)
         assert np.array_equal(gm, np.broadcast_to(gm[0], gm.shape))          # every chain follows the same arithmetic
 
