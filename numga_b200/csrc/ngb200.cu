@@ -1771,7 +1771,20 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                 else appendf(s, "%s      NGB_ST(%s, y[%d]);\n", ind, a.c_str(), g.yoff[j] + c);
             }
         }
-        appendf(s, "%s    }\n%s  }\n%s}\n%s__syncthreads();\n", ind, ind, ind, ind);
+        appendf(s, "%s    }\n%s  }\n%s}\n", ind, ind, ind);
+        // A barrier separates this phase from the next one in program order -- unless both run over the same domain and
+        // touch shared buffers only at their own item (no index): then thread i of the next phase reads exactly what
+        // thread i wrote here (same thread: same item mapping), and no other thread's data.
+        const int last = (int)Q.phases.size() - 1;
+        const int next = ((int)k + 1 == Q.loop_end && Q.loop_end > Q.loop_begin) ? -1 : ((int)k < last ? (int)k + 1 : -1);
+        auto direct_only = [&](const PipePhase &q) {
+            for (const ngb200_bind &b : q.in) if (b.kind == NGB200_BIND_SHARED && b.index >= 0) return false;
+            for (const ngb200_bind &b : q.out) if (b.kind == NGB200_BIND_SHARED && b.index >= 0) return false;
+            return true;
+        };
+        const bool elide = next >= 0 && Q.phases[next].domain == ph.domain && direct_only(ph) && direct_only(Q.phases[next]) &&
+                           env_int("NGB200_PIPE_ELIDE", 1);
+        if (!elide) appendf(s, "%s__syncthreads();\n", ind);
     };
     // L2 prefetch of what the LATER phases of this tile read from global memory (per-item constants and tables that are
     // not parked in shared memory): issued before the first phase, so that their DRAM latency overlaps the load phase
@@ -2202,7 +2215,7 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
     if (chunk_items <= 0) chunk_items = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 128) * (1 << 20) / (per_item ? per_item : 1);
     chunk_items = (chunk_items + 255) / 256 * 256;
     if (chunk_items > batch) chunk_items = (batch + 255) / 256 * 256;
-    const int n_slots = (int)std::min<int64_t>(env_int("NGB200_HOST_STREAMS", 4), (batch + chunk_items - 1) / chunk_items);
+    const int n_slots = (int)std::min<int64_t>(env_int("NGB200_HOST_STREAMS", 8), (batch + chunk_items - 1) / chunk_items);
 
     std::lock_guard<std::mutex> pipe_lock(P->host_mu);      // one host run per program at a time (shared staging)
     if (!P->host) P->host = new HostPipe;
@@ -2268,7 +2281,7 @@ extern "C" int ngb200_host_copy_control(void *host_in, int64_t in_bytes, void *h
     rc = current_device(&dev, device);
     if (rc) return rc;
     if (chunk_bytes <= 0) chunk_bytes = (int64_t)env_int("NGB200_HOST_CHUNK_MB", 128) * (1 << 20) / 2;   // in + out = one pipeline chunk
-    if (streams <= 0) streams = env_int("NGB200_HOST_STREAMS", 4);
+    if (streams <= 0) streams = env_int("NGB200_HOST_STREAMS", 8);
     struct Slot { CUstream s = nullptr; CUdeviceptr din = 0, dout = 0; };
     static std::mutex mu;
     static std::vector<Slot> slots;

@@ -324,8 +324,9 @@ class ChainStep:
     Needs the block structure `replicate_chains` produces (independent chains laid out one after the other); the
     formulas are the same traced python bodies `FusedStep` uses.  `integrate(bodies, dt)` = `unroll` sub-steps of dt."""
 
-    def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0):
-        from numga_b200.pipeline import Pipeline
+    def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0, exploit_zeros=False):
+        from numga_b200.pipeline import Pipeline, compact_operator, expand_operator
+        from numga_b200.backend import _OperatorKey, kernel_space
         import torch
         ctx = self.context = bodies.motor.context
         self.sets, self.unroll = list(constraint_sets), int(unroll)
@@ -339,30 +340,48 @@ class ChainStep:
             # one thread per constraint in the constraint phases (every warp busy there: they are 60 % of the work), two
             # bodies per thread in the body phases: 8.07 vs 6.60 G body-steps/s against one thread per body
             threads_per_tile = min(1024, -(-max([c * k for c in per_block] + [-(-block * k // 2)]) // 32) * 32)
+        # Which entries of the bound operators (inertia, inverse inertia, anchor maps) can be non-zero.  By default that is
+        # what the integer tables say (`op.mask`; an `inverse()` is dense).  With `exploit_zeros` the tables' VALUES are
+        # inspected once, here: entries that are exactly zero for every item are compiled out (never loaded, never
+        # multiplied) -- the "numerical sparsity of inertia tensors" the reference notes but cannot use
+        # (numga/backend/torch/operator.py:60-64).  The kernel is then specific to this zero pattern; `integrate` checks
+        # that it is handed the same (unmodified) tables.
+        self.exploit_zeros = bool(exploit_zeros)
+
+        def mask_of(op):
+            if not self.exploit_zeros or ctx.compile_only:        # (compile-only contexts hold uninitialised tables)
+                return op.mask
+            flat = op.flat.reshape(-1, op.flat.shape[-1])
+            return op.mask & (flat != 0).any(dim=0).cpu().numpy().reshape(op.kshape)
+        inv_mask, inertia_mask = mask_of(bodies.inertia_inv), mask_of(bodies.inertia)
+        map_masks = [mask_of(c.anchors_map) for c in self.sets]
+        self._inspected = [(t.data_ptr(), t._version) for t in (bodies.inertia.flat, bodies.inertia_inv.flat)]
+        inv_axes = bodies.inertia_inv.axes
         S = ctx.subspace
         names = ['body'] + [f'set{j}' for j in range(len(self.sets))]
         pipe = Pipeline(ctx, dict(zip(names, [block * k] + [c * k for c in per_block])), threads_per_tile=threads_per_tile)
-        from numga_b200.backend import _OperatorKey
-        inv_space = _OperatorKey(bodies.inertia_inv.axes, bodies.inertia_inv.mask)
-        inertia_space = _OperatorKey(bodies.inertia.axes, bodies.inertia.mask)
+        inv_space = _OperatorKey(inv_axes, inv_mask)
+        inv_compact = kernel_space((int(inv_mask.sum()),))          # shared memory holds the non-zero entries only
+        inertia_space = _OperatorKey(bodies.inertia.axes, inertia_mask)
         g_motor, g_rate = pipe.array('motor', S.even_grade(), 'body'), pipe.array('rate', S.bivector(), 'body')
         g_fm = pipe.array('first_moment', bodies.first_moment.subspace, 'body')
         g_inertia, g_inv = pipe.array('inertia', inertia_space, 'body'), pipe.array('inertia_inv', inv_space, 'body')
         g_damping, g_gravity = pipe.array('damping', bodies.damping.subspace, 'body'), pipe.array('gravity', bodies.gravity.subspace, 'body')
         o_motor, o_rate = pipe.array('motor_out', S.even_grade(), 'body'), pipe.array('rate_out', S.bivector(), 'body')
         s_motor, s_rate = pipe.buffer(S.even_grade(), 'body'), pipe.buffer(S.bivector(), 'body')
-        s_old, s_inv = pipe.buffer(S.even_grade(), 'body'), pipe.buffer(inv_space, 'body')
+        s_old, s_inv = pipe.buffer(S.even_grade(), 'body'), pipe.buffer(inv_compact, 'body')
         dt = pipe.param(0)
+        unpack = lambda c: expand_operator(ctx, inv_axes, inv_mask, c)
 
-        from numga_b200.pipeline import operator_values
-        pipe.phase('body', lambda m, r, inv: (m, r, operator_values(inv)), [g_motor, g_rate, g_inv], [s_motor, s_rate, s_inv])
+        pipe.phase('body', lambda m, r, inv: (m, r, compact_operator(inv, inv_mask)), [g_motor, g_rate, g_inv], [s_motor, s_rate, s_inv])
 
-        def pre(motor, rate, first_moment, inertia, inertia_inv, damping, gravity, dt):
-            new = Body(motor, rate, first_moment, inertia, inertia_inv, damping, gravity).pre_integrate(dt)
+        def pre(motor, rate, first_moment, inertia, inv_c, damping, gravity, dt):
+            new = Body(motor, rate, first_moment, inertia, unpack(inv_c), damping, gravity).pre_integrate(dt)
             return new.motor, new.rate, motor
         pipe.phase('body', pre, [s_motor, s_rate, g_fm, g_inertia, s_inv, g_damping, g_gravity, dt], [s_motor, s_rate, s_old])
 
         def apply(m0, m1, inv0, inv1, a0, a1, compliance, dt):
+            inv0, inv1 = unpack(inv0), unpack(inv1)
             w0, w1 = m0 >> a0, m1 >> a1
             forque = w0 & w1
             magnitude = forque.norm()
@@ -375,6 +394,7 @@ class ChainStep:
             return m, motor_relative_step(m.reverse(), old_motor.reverse()) / dt
 
         def v_apply(m0, m1, r0, r1, inv0, inv1, map0, map1, compliance, dt):
+            inv0, inv1 = unpack(inv0), unpack(inv1)
             v0, v1 = m0 >> map0(r0), m1 >> map1(r1)
             forque = -(v0 * 0.5 + v1 * -0.5)
             magnitude = forque.norm()
@@ -386,7 +406,7 @@ class ChainStep:
         for j, c in enumerate(self.sets):
             i0, i1 = pipe.index(f'set{j}/i0', f'set{j}'), pipe.index(f'set{j}/i1', f'set{j}')
             a0, a1 = pipe.array(f'set{j}/a0', c.anchors.subspace, f'set{j}'), pipe.array(f'set{j}/a1', c.anchors.subspace, f'set{j}')
-            map_space = _OperatorKey(c.anchors_map.axes, c.anchors_map.mask)
+            map_space = _OperatorKey(c.anchors_map.axes, map_masks[j])
             m0, m1 = pipe.array(f'set{j}/map0', map_space, f'set{j}'), pipe.array(f'set{j}/map1', map_space, f'set{j}')
             comp = pipe.array(f'set{j}/compliance', c.compliance.subspace, f'set{j}')
             per_set.append((i0, i1, a0, a1, m0, m1, comp))
@@ -412,6 +432,11 @@ class ChainStep:
     def integrate(self, bodies, dt):
         from numga_b200.backend import soa_empty
         ctx = self.context
+        if self.exploit_zeros:
+            seen = [(t.data_ptr(), t._version) for t in (bodies.inertia.flat, bodies.inertia_inv.flat)]
+            if seen != self._inspected:
+                raise ValueError('ChainStep(exploit_zeros=True) was specialised on the zero pattern of other inertia tables; '
+                                 'build a new ChainStep for these bodies')
         n = bodies.motor.shape[0]
         motor = ctx.mvtype(ctx, bodies.motor.subspace, soa_empty(8, (n,), ctx.dtype, ctx.device))
         rate = ctx.mvtype(ctx, bodies.rate.subspace, soa_empty(6, (n,), ctx.dtype, ctx.device))

@@ -33,6 +33,31 @@ def operator_values(op):
     return TracedMultiVector(op.context, kernel_space(op.kshape), op._flat)
 
 
+def compact_operator(op, mask=None):
+    """Inside a traced phase: the structurally non-zero kernel entries of a bound operator (C order over `mask`) as a
+    multivector over a compact kernel space -- what gets parked in shared memory."""
+    from numga_b200.backend import kernel_space
+    from numga_b200.multivector import TracedMultiVector
+    from numga_b200.trace import SymArray
+    mask = op.mask if mask is None else mask
+    pos = np.flatnonzero(np.asarray(mask).reshape(-1))
+    regs = op._flat.regs
+    return TracedMultiVector(op.context, kernel_space((len(pos),)), SymArray(op._flat.trace, [regs[p] for p in pos]))
+
+
+def expand_operator(context, axes, mask, compact):
+    """Inverse of `compact_operator`: a bound operator over `axes` whose masked entries are the components of the traced
+    multivector `compact` and whose other entries are the constant 0."""
+    from numga_b200.backend import B200DenseOperator
+    from numga_b200.trace import SymArray
+    trace = compact.values.trace
+    zero = trace.const(0.0)
+    flat = [zero] * int(np.prod(np.asarray(mask).shape))
+    for j, p in enumerate(np.flatnonzero(np.asarray(mask).reshape(-1))):
+        flat[p] = compact.values.regs[j]
+    return B200DenseOperator(context, axes, SymArray(trace, flat), np.asarray(mask))
+
+
 class Ref:
     """A pipeline operand: a global array / index array / shared buffer, optionally addressed through an index."""
 
