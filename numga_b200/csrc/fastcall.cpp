@@ -8,6 +8,7 @@
 // torch is used for what it is in this project: device memory and streams.  The kernels are launched through the
 // C ABI of libnumga_b200.so (function pointers handed over at start-up; no link-time dependency).
 #include <ATen/ATen.h>
+#include <ATen/core/grad_mode.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
@@ -58,9 +59,11 @@ static py::object launch(FastPlan &p, const std::vector<at::Tensor> &inputs, con
     void *in_ptrs[32];
     void *out_ptrs[32];
     if (nin > 32 || nout > 32) return py::none();
+    const bool grad_mode = at::GradMode::is_enabled();
     for (size_t k = 0; k < nin; ++k) {
         const at::Tensor &t = inputs[k];
         if (t.scalar_type() != p.dtype || !t.is_cuda() || t.get_device() != p.device) return py::none();
+        if (grad_mode && t.requires_grad()) return py::none();        // differentiable call: the python path builds the autograd node
         const auto sz = t.sizes(), st = t.strides();
         const auto &es = p.in_sizes[k], &et = p.in_strides[k];
         if (sz.size() != es.size()) return py::none();
