@@ -57,7 +57,10 @@ extern "C" {
                               outer_stride, so nothing has to be expanded in memory */
 #define NGB200_REDUCED 3   /* outputs only: ONE multivector = the sum of the per-item results over the batch
                               (warp shuffle + shared + one atomicAdd per CTA and component); the caller zeroes it.
-                              Used for the gradient of a broadcast operand. */
+                              Used for the gradient of a broadcast operand and for sums over the batch axis.  The CTA
+                              partial sums meet in floating-point atomicAdd, so the result is reproducible only up to
+                              the rounding of a sum taken in a run-dependent order (relative ~1e-7 fp32 / 1e-16 fp64
+                              per addend); not supported by ngb200_program_run_host. */
 
 /* ---- straight-line program IR --------------------------------------------------------------
  * A program maps, independently for every batch item, the components of its input multivectors

@@ -1,12 +1,15 @@
 """Compile (NVRTC, sm_100a) the generated kernels of the standard programs into the in-tree cubin cache.
 
-Runs without a GPU: contexts are created in compile-only mode and the expressions of the case catalogue
-(tests/cases.py), of bench.py, of the physics example and of the ported reference identity tests are executed on
-uninitialised host tensors, so that every kernel they need — per-method eager kernels, fused `jit` kernels,
-operator-table kernels — is generated, compiled and stored under numga_b200/_kcache/.  On the GPU box these are
-cache hits (no JIT there).  The work is a list of independent jobs spread over a process pool (the cache is written
-atomically, so workers never collide).
+Runs without a GPU: contexts are created in compile-only mode and the expressions of bench.py, of the physics example
+and of the gather / scatter paths are executed on uninitialised host tensors, so that every kernel they need --
+per-method eager kernels, fused `jit` kernels, operator-table kernels, pipeline kernels -- is generated, compiled and
+stored under numga_b200/_kcache/.  On the GPU box these are cache hits (no JIT there).  The work is a list of
+independent jobs spread over a process pool (the cache is written atomically, so workers never collide).
+
+The test-suite's own programs (case catalogue, ported identity tests) are pre-compiled by `tests/prewarm_jobs.py`, which
+plugs into the same pool through `prewarm(extra=...)`; this module does not import anything from tests/.
 """
+import importlib
 import os
 import sys
 
@@ -14,25 +17,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _paths():
-    for p in (ROOT, os.path.join(ROOT, 'tests')):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
 
 
 def bench_programs(ctx_of):
-    """The fused programs bench.py times (kept in one place so build() and bench agree)."""
+    """The fused programs bench.py times, fast and faithful (kept in one place so build() and bench agree)."""
     import torch
     out = []
-    pga32 = ctx_of((3, 0, 1), torch.float32, 'fast')
-    S = pga32.subspace
-    out.append((pga32, lambda r, p: r >> p, [(S.even_grade(), 'single'), (S.antivector(), 'batch')]))
-    out.append((pga32, lambda a, b: a * b, [(S.even_grade(), 'batch'), (S.even_grade(), 'batch')]))
-    out.append((pga32, lambda b: b.exp().normalized().motor_log(), [(S.bivector(), 'batch')]))
+    for mode in ('fast', 'faithful'):
+        pga32 = ctx_of((3, 0, 1), torch.float32, mode)
+        S = pga32.subspace
+        out.append((pga32, lambda r, p: r >> p, [(S.even_grade(), 'single'), (S.antivector(), 'batch')]))
+        out.append((pga32, lambda a, b: a * b, [(S.even_grade(), 'batch'), (S.even_grade(), 'batch')]))
+        out.append((pga32, lambda b: b.exp().normalized().motor_log(), [(S.bivector(), 'batch')]))
+        cga = ctx_of((4, 1, 0), torch.float32, mode)
+        F = cga.subspace.full()
+        out.append((cga, lambda a, b: a * b, [(F, 'batch'), (F, 'batch')]))
     pga64 = ctx_of((3, 0, 1), torch.float64, 'fast')
     out.append((pga64, lambda b: b.exp().normalized().motor_log(), [(pga64.subspace.bivector(), 'batch')]))
-    cga = ctx_of((4, 1, 0), torch.float32, 'fast')
-    F = cga.subspace.full()
-    out.append((cga, lambda a, b: a * b, [(F, 'batch'), (F, 'batch')]))
     return out
 
 
@@ -59,20 +62,10 @@ def _run(ctx, fn, specs, batch=8):
 
 
 def jobs():
-    """(kind, argument) pairs; every job is independent of the others."""
-    _paths()
+    """(kind, argument) pairs of the product-side programs; every job is independent of the others."""
     out = [('bench', None), ('gather', None)]
     out += [('physics', (dt, mode)) for dt in ('float32', 'float64') for mode in ('fast', 'faithful')]
-    if os.path.isdir(os.path.join(ROOT, 'tests')):
-        from cases import CASES
-        out += [('case', c[0]) for c in CASES]
-        import test_reference_identities as T
-        for k, (fn, params) in enumerate(T.GPU_MATRIX):
-            out += [('identity', (k, descr)) for descr in params]
-        out += [('identity_single', k) for k in range(len(T.GPU_SINGLES))]
-    # biggest first: the 5-dimensional inverse sweeps dominate the wall clock
-    weight = lambda j: -(sum(j[1][1]) if j[0] == 'identity' else 0)
-    return sorted(out, key=weight)
+    return out
 
 
 def run_job(job):
@@ -106,22 +99,6 @@ def run_job(job):
         for bpt in (None, 84):          # the chain-resident pipeline kernel: default tile and the partial-tile test's
             ChainStep(bodies, sets, bodies_per_tile=bpt).integrate(bodies, 1 / 200)
         bodies.kinetic_energy()
-    elif kind == 'case':
-        from cases import CASE_BY_NAME
-        name, pqr, specs, scale, fn = CASE_BY_NAME[arg]
-        for dtype in (torch.float32, torch.float64):
-            for mode in ('fast', 'faithful'):
-                ctx = ctx_of(pqr, dtype, mode)
-                _run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
-    elif kind in ('identity', 'identity_single'):
-        import test_reference_identities as T
-        try:
-            if kind == 'identity':
-                T.GPU_MATRIX[arg[0]][0](arg[1], 'compile')
-            else:
-                T.GPU_SINGLES[arg]('compile')
-        except AssertionError:
-            pass        # value assertions mean nothing on uninitialised memory; the kernels up to there are compiled
     return job
 
 
@@ -129,17 +106,37 @@ def rt_cache_dir():
     return os.environ.get('NGB200_CACHE_DIR') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '_kcache')
 
 
-def prewarm(workers=None):
-    """Returns the number of cubins in the cache afterwards."""
+def _dispatch(item):
+    """Pool entry point: (module name | None, job).  Extra providers are modules with `jobs()` and `run_job(job)`."""
+    module, job = item
+    _paths()
+    if module is None:
+        return run_job(job)
+    path, name = module
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    return importlib.import_module(name).run_job(job)
+
+
+def prewarm(workers=None, extra=()):
+    """Compile everything; `extra` = [(directory, module name)] of additional job providers.  Returns the number of
+    cubins in the cache afterwards."""
     import multiprocessing as mp
-    todo = jobs()
+    _paths()
+    todo = [(None, j) for j in jobs()]
+    for path, name in extra:
+        if path not in sys.path:
+            sys.path.insert(0, path)
+        mod = importlib.import_module(name)
+        todo += [((path, name), j) for j in mod.jobs()]
+    todo.sort(key=lambda t: -getattr(importlib.import_module(t[0][1]), 'weight', lambda j: 0)(t[1]) if t[0] else -1000)
     workers = workers or max(1, min(len(todo), os.cpu_count() or 1, 16))
     if workers == 1:
-        for j in todo:
-            run_job(j)
+        for t in todo:
+            _dispatch(t)
     else:
         with mp.get_context('spawn').Pool(workers) as pool:
-            for _ in pool.imap_unordered(run_job, todo, chunksize=1):
+            for _ in pool.imap_unordered(_dispatch, todo, chunksize=1):
                 pass
     d = rt_cache_dir()
     return len([f for f in os.listdir(d) if f.endswith('.cubin')]) if os.path.isdir(d) else 0
