@@ -547,6 +547,10 @@ def run_cfg5(torch, B200Context, rank, peak, n_target=1 << 24, unroll=10, faithf
     from numga_b200 import runtime as rt
     from numga_b200.examples import physics as X
     out = []
+    issue = {}
+    ip = os.path.join(ROOT, 'profiles', 'r02_issue_slots.json')
+    if os.path.exists(ip):
+        issue = json.load(open(ip))
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
         npd = np.float32 if tag == 'f32' else np.float64
         es = 4 if tag == 'f32' else 8
@@ -624,6 +628,10 @@ def run_cfg5(torch, B200Context, rank, peak, n_target=1 << 24, unroll=10, faithf
                           f'{u} sub-step(s) per launch', n_bodies * u, ms, state_once / u, peak, unit='body-steps/s',
                           parity_ok=parity[label]['ok'], parity=parity[label], kernel_launches_per_step=launches,
                           sub_steps_per_launch=u, bodies=n_bodies)
+                if not zeros:
+                    e['roofline']['issue_slot_utilisation_ncu'] = issue.get(f"cfg5_{tag}_{'one_substep' if u == 1 else 'ten_substeps'}_per_launch")
+                    if u > 1:
+                        e['roofline']['bound'], e['roofline']['compute_bound'] = 'issue slots', True
                 if zeros:
                     e['note'] = ('supplementary: entries of the inertia / inverse-inertia / anchor-map tables that are exactly zero for '
                                  'EVERY body (found by inspecting the tables at set-up; 6 of 36 in the inverse inertia of this example) '
