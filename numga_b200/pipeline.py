@@ -161,9 +161,41 @@ class CompiledPipeline:
             assert domain < 0 or bs == 1 or _prod(v.shape[:-1]) == 1, f'{name}: not structure-of-arrays'
         return keep, ops
 
+    def validate(self, arrays, items):
+        """Bounds check of every index operand (the kernel itself does none): rows addressed in a shared buffer must
+        fall inside the tile of the item that addresses them, rows addressed in a global array inside that array.  Done
+        once per index tensor (identity + version) from `launch`; costs a few small torch reductions."""
+        pipe = self.pipe
+        counts = [int(items[d]) for d in pipe.domains]
+        seen = self.__dict__.setdefault('_validated', set())
+        for ir, d, ins, outs in self.phases:
+            for kind, slot, index in list(ins) + list(outs):
+                if index < 0:
+                    continue
+                name = pipe.globals[index][0]
+                idx = arrays[name]
+                target = pipe.shared[slot][1] if kind == rt.BIND_SHARED else pipe.globals[slot][2]
+                key = (name, kind, target, idx.data_ptr(), idx._version, counts[d], counts[target])
+                if key in seen:
+                    continue
+                n = counts[d]
+                assert idx.numel() >= n, f'{name}: {idx.numel()} indices for {n} items'
+                rows = idx.reshape(-1)[:n]
+                ok = (rows >= 0) & (rows < counts[target])
+                if kind == rt.BIND_SHARED:
+                    ipt_src, ipt_dst = pipe.items_per_tile[d], pipe.items_per_tile[target]
+                    tile = torch.div(torch.arange(n, device=rows.device), ipt_src, rounding_mode='floor')
+                    local = rows - tile * ipt_dst
+                    ok &= (local >= 0) & (local < ipt_dst)
+                if n and not bool(ok.all()):
+                    raise ValueError(f'pipeline index operand {name!r} addresses rows outside its tile / array '
+                                     f'(first offender: item {int((~ok).nonzero()[0])})')
+                seen.add(key)
+
     def launch(self, arrays, items, repeat=1, params=()):
         """arrays: {name: multivector | bound operator | int64 tensor}; items: {domain: total item count}."""
         ctx, pipe = self.context, self.pipe
+        self.validate(arrays, items)
         counts = [int(items[d]) for d in pipe.domains]
         n_tiles = max(-(-c // ipt) for c, ipt in zip(counts, pipe.items_per_tile))
         keep, ops = self.operands(arrays)

@@ -463,3 +463,54 @@ def test_eager_fast_path_repeated_calls_layout_changes_and_scalars():
     want = (c * ctx.multivector.motor(half.numpy())).numpy()
     for _ in range(3):
         assert np.array_equal((c * half).numpy(), want)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_generated_gather_scatter_and_batch_sums_on_device(dtype):
+    """`mv[index]`, `mv.at[index].set(rows)`, `sum` / `mean` over batch axes on the GPU: generated kernels (identity
+    programs with INDEXED operands, slice-adding programs, batch-reduced outputs) against torch on the same data."""
+    ctx = _ctx((3, 0, 1), dtype)
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((5000, 8)).astype(dtype)
+    m = ctx.multivector.motor(x)
+    idx = torch.as_tensor(rng.integers(-5000, 5000, size=(3, 1111)), device='cuda')
+    got = m[idx]
+    assert got.shape == (3, 1111) and np.array_equal(got.numpy(), x[idx.cpu().numpy()])
+    perm = torch.as_tensor(rng.permutation(5000)[:777], device='cuda')
+    rows = ctx.multivector.motor(rng.standard_normal((777, 8)).astype(dtype))
+    new = m.at[perm].set(rows)
+    want = x.copy()
+    want[perm.cpu().numpy()] = rows.numpy()
+    assert np.array_equal(new.numpy(), want) and np.array_equal(m.numpy(), x)
+    tol = 1e-5 if dtype == np.float32 else 1e-13
+    q = ctx.multivector.antivector(rng.standard_normal((7, 333, 4)).astype(dtype))
+    for axis in (0, 1, -2):
+        assert np.abs(q.sum(axis).numpy() - q.numpy().sum(axis)).max() < tol * 30
+        assert np.abs(q.mean(axis).numpy() - q.numpy().mean(axis)).max() < tol
+    flat = ctx.multivector.antivector(rng.standard_normal((100003, 4)).astype(dtype))
+    ref = flat.numpy().astype(np.float64).sum(0)
+    assert np.abs(flat.sum(0).numpy() - ref).max() < (2e-2 if dtype == np.float32 else 1e-9) and flat.sum(0).shape == ()
+    assert any(k[0] == ('gather',) for k in ctx.engine.cache) and any(k[0][0] == 'reduce' for k in ctx.engine.cache)
+
+
+def test_chain_step_partial_tiles_zero_pattern_and_validation():
+    """ChainStep on a batch whose last tile is partial, for several tile sizes, with and without `exploit_zeros`, against
+    the six-kernel arrangement; and the host-side refusal of index operands that leave their tile."""
+    from numga_b200 import B200Context
+    from numga_b200.examples.physics import ChainStep, FusedStep, replicate_chains, setup_bodies
+    for tdt, tol in ((torch.float32, 1e-6), (torch.float64, 1e-14)):
+        ctx = B200Context('x+y+z+w0', dtype=tdt, device='cuda:0')
+        bodies, sets = setup_bodies(ctx, n_bodies=12)
+        big, bsets = replicate_chains(bodies, sets, 45)                 # 45 chains: 32 + 13 at 384 bodies per tile
+        big = big.copy(rate=big.rate + ctx.multivector.bivector(0.3 * np.random.default_rng(2).standard_normal((540, 6))))
+        fs = FusedStep(big, bsets)
+        ref = fs.integrate(fs.integrate(big, 1 / 200), 1 / 200)
+        for bpt, zeros in ((None, False), (84, False), (None, True)):
+            got = ChainStep(big, bsets, unroll=2, bodies_per_tile=bpt, exploit_zeros=zeros).integrate(big, 1 / 200)
+            for f in ('motor', 'rate'):
+                g, r = getattr(got, f).numpy(), getattr(ref, f).numpy()
+                assert np.isfinite(g).all()
+                assert np.abs(g - r).max() <= (0 if not zeros else tol * 200) * max(1.0, np.abs(r).max()), (tdt, bpt, zeros, f)
+    scrambled = [type(bsets[0])(bsets[0].body_idx.flip(1), bsets[0].anchors, bsets[0].compliance), bsets[1]]
+    with pytest.raises(ValueError):
+        ChainStep(big, scrambled)

@@ -144,3 +144,47 @@ def test_batch_axis_sums_and_row_gathers_are_generated_kernels():
         idx2 = torch.tensor([[0, 1, 2], [-3, 33, 5]])
         assert np.array_equal(flat[idx2].numpy(), x.reshape(35, 4)[idx2.numpy()]) and flat[idx2].shape == (2, 3)
         assert any(k[0] == ('gather',) for k in ctx.engine.cache)
+
+
+def test_at_set_of_whole_rows_is_a_generated_copy_and_scatter():
+    """`mv.at[index_array].set(rows)` returns a modified copy written by generated kernels (copy + INDEXED-output
+    scatter); the original is untouched; other index forms keep torch semantics."""
+    from cpu_emulation import emulate_launches, emulated_context
+    rng = np.random.default_rng(4)
+    with emulate_launches():
+        ctx = emulated_context((3, 0, 1), torch.float64)
+        x = rng.standard_normal((20, 8))
+        m = ctx.multivector.motor(x)
+        idx = np.array([[3, 7, 0], [19, -2, 5]])
+        rows = ctx.multivector.motor(rng.standard_normal((2, 3, 8)))
+        new = m.at[idx].set(rows)
+        want = x.copy()
+        want[idx] = rows.numpy()
+        assert np.array_equal(new.numpy(), want) and np.array_equal(m.numpy(), x) and new.subspace is m.subspace
+        assert any(k[0] == ('scatter_rows',) for k in ctx.engine.cache) and any(k[0] == ('copy_rows',) for k in ctx.engine.cache)
+        one = m.at[4].set(ctx.multivector.motor(np.ones(8)))              # scalar index: torch path
+        assert np.array_equal(one.numpy()[4], np.ones(8)) and np.array_equal(one.numpy()[5], x[5])
+
+
+def test_pipeline_index_operands_are_bounds_checked_on_the_host():
+    """The pipeline kernel trusts its index operands; `CompiledPipeline.validate` (run by `launch`) refuses rows that
+    fall outside the addressing item's tile (shared buffers) or outside the array (global operands)."""
+    from numga_b200 import B200Context
+    from numga_b200.pipeline import Pipeline
+    ctx = B200Context((3, 0, 1), device='cpu', compile_only=True)
+    S = ctx.subspace
+    pipe = Pipeline(ctx, {'node': 8, 'edge': 4})
+    a, out = pipe.array('a', S.vector(), 'node'), pipe.array('out', S.vector(), 'edge')
+    i0, i1 = pipe.index('i0', 'edge'), pipe.index('i1', 'edge')
+    buf = pipe.buffer(S.vector(), 'node')
+    pipe.phase('node', lambda x: x * 2, [a], [buf])
+    pipe.phase('edge', lambda x, y: x - y, [buf[i0], buf[i1]], [out])
+    cp = pipe.build()
+    arrays = {'a': ctx.multivector.vector(torch.zeros(16, 4)), 'out': ctx.multivector.vector(torch.zeros(8, 4)),
+              'i0': torch.tensor([0, 1, 2, 3, 8, 9, 10, 11]), 'i1': torch.tensor([7, 6, 5, 4, 15, 14, 13, 12])}
+    cp.launch(arrays, {'node': 16, 'edge': 8})                               # compile-only: validated, not launched
+    bad = dict(arrays, i1=torch.tensor([7, 6, 5, 4, 15, 14, 13, 3]))         # edge 7 (tile 1) reaches into tile 0
+    with pytest.raises(ValueError, match="'i1'"):
+        cp.launch(bad, {'node': 16, 'edge': 8})
+    with pytest.raises(ValueError, match="'i0'"):
+        cp.launch(dict(arrays, i0=torch.tensor([0, 1, 2, 3, 8, 9, 10, 16])), {'node': 16, 'edge': 8})
