@@ -254,6 +254,10 @@ struct Gen {
     std::string suffix;                       // "" -> ngb_uniform / ngb_body
     std::string params_type = "Params";
     std::vector<std::string> bcast_ref;       // per input k: "p.in[k]"-like expression with .ptr / .cs
+    // pipelines only: inputs that are NOT preloaded into x[] but re-read from shared memory at every use (wide tables
+    // in fp64: the registers they would occupy for the whole phase are worth more than the extra LDS); value = slot in xp[]
+    std::vector<int> remat;
+    int n_remat = 0;
 
     explicit Gen(const ngb200_program &p)
         : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {
@@ -267,7 +271,11 @@ struct Gen {
         if (I.op == NGB200_OP_CONST) return literal(P.consts[I.a], P.dtype);
         if (in_body) {
             if (uniform[v]) return "u[" + std::to_string(uslot[v]) + "]";
-            if (I.op == NGB200_OP_INPUT) return "x[" + std::to_string(xoff[I.a] + I.b) + "]";
+            if (I.op == NGB200_OP_INPUT) {
+                if (I.a < (int)remat.size() && remat[I.a] >= 0)
+                    return "ngb_lds(xp[" + std::to_string(remat[I.a]) + "] + " + std::to_string(I.b) + ")";
+                return "x[" + std::to_string(xoff[I.a] + I.b) + "]";
+            }
             return "r" + std::to_string(v);
         }
         return "q" + std::to_string(v);
@@ -581,8 +589,12 @@ struct Gen {
 
     // the per-item straight-line body
     void emit_body(std::string &s, int *nl, std::vector<int> *stored_out = nullptr) const {
-        appendf(s, "__device__ __forceinline__ void ngb_body%s(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
-                suffix.c_str(), NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
+        if (n_remat > 0)
+            appendf(s, "__device__ __forceinline__ void ngb_body%s(const T (&x)[%d], const T* const (&xp)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
+                    suffix.c_str(), NX > 0 ? NX : 1, n_remat, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
+        else
+            appendf(s, "__device__ __forceinline__ void ngb_body%s(const T (&x)[%d], const T (&u)[%d], T (&y)[%d]) {\n",
+                    suffix.c_str(), NX > 0 ? NX : 1, NU > 0 ? NU : 1, NY > 0 ? NY : 1);
         for (int v : order) {
             ++*nl;
             if (fused_into[v] >= 0) continue;      // this multiply lives inside the FMA of its consumer
@@ -1646,6 +1658,12 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         const int need = g.max_live * (f64 ? 2 : 1) + 24;
         if (need > max_need) max_need = need;
         total_nu += g.NU;
+        // wide shared-memory tables are re-read at every use instead of being held in registers for the whole phase
+        g.remat.assign(ph.in.size(), -1);
+        if (Q.records && env_int("NGB200_PIPE_REMAT", f64 ? 1 : 0))
+            for (size_t j = 0; j < ph.in.size(); ++j)
+                if (ph.in[j].kind == NGB200_BIND_SHARED && ph.prog->in_width[j] >= env_int("NGB200_PIPE_REMAT_WIDTH", 16))
+                    g.remat[j] = g.n_remat++;
     }
     max_need += total_nu * (f64 ? 2 : 1);
     int minb = 65536 / (Q.tpb * (max_need > 32 ? max_need : 32));
@@ -1653,6 +1671,10 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
     if (env_int("NGB200_PIPE_MINB", 0) > 0) Q.minb = env_int("NGB200_PIPE_MINB", 0);
     gens[0]->emit_prelude(s, 1, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), false);
     appendf(s, "#define NGB_TPB %d\n", Q.tpb);
+    if (f64)
+        s += "__device__ __forceinline__ double ngb_lds(const double* p) { double r; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(r) : \"r\"((unsigned)__cvta_generic_to_shared(p)) : \"memory\"); return r; }\n";
+    else
+        s += "__device__ __forceinline__ float ngb_lds(const float* p) { float r; asm volatile(\"ld.shared.f32 %0, [%1];\" : \"=f\"(r) : \"r\"((unsigned)__cvta_generic_to_shared(p)) : \"memory\"); return r; }\n";
     s += "struct PG { T* ptr; long long cs; };\n";
     appendf(s, "struct PParams { PG g[%d]; const long long* idx[%d]; double scal[%d]; long long n[%d]; long long n_tiles; int repeat; };\n",
             Q.n_value_globals > 0 ? Q.n_value_globals : 1, Q.n_index_globals > 0 ? Q.n_index_globals : 1,
@@ -1723,8 +1745,14 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                      r.c_str(), VW, Q.rec_off[b.slot]);
             return buf;
         };
+        if (g.n_remat > 0) {
+            appendf(s, "%s      const T* xp[%d];\n", ind, g.n_remat);
+            for (size_t j = 0; j < ph.in.size(); ++j)
+                if (g.remat[j] >= 0) appendf(s, "%s      xp[%d] = %s;\n", ind, g.remat[j], record_base(ph.in[j]).c_str());
+        }
         for (size_t j = 0; j < ph.in.size(); ++j) {
             if (ph.prog->in_mode[j] == NGB200_BROADCAST) continue;
+            if (g.remat[j] >= 0) continue;                  // re-read at every use inside the body
             if (Q.records && ph.in[j].kind == NGB200_BIND_SHARED) {
                 const int w = ph.prog->in_width[j];
                 std::string base = record_base(ph.in[j]);
@@ -1748,7 +1776,8 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                 else appendf(s, "%s      x[%d] = NGB_LD(%s);\n", ind, g.xoff[j] + c, a.c_str());
             }
         }
-        appendf(s, "%s      ngb_body_%zu(x, u%zu, y);\n", ind, k, k);
+        if (g.n_remat > 0) appendf(s, "%s      ngb_body_%zu(x, xp, u%zu, y);\n", ind, k, k);
+        else appendf(s, "%s      ngb_body_%zu(x, u%zu, y);\n", ind, k, k);
         for (size_t j = 0; j < ph.out.size(); ++j) {
             if (Q.records && ph.out[j].kind == NGB200_BIND_SHARED) {
                 const int w = ph.prog->out_width[j];

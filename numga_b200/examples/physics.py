@@ -418,7 +418,13 @@ class ChainStep:
                        [s_rate[i0], s_rate[i1]])
         n_loop = 2 + 2 * len(self.sets)
         pipe.phase('body', lambda m, r: (m, r), [s_motor, s_rate], [o_motor, o_rate])
-        self.compiled = pipe.build(loop=(1, 1 + n_loop))
+        from numga_b200 import runtime as _rt
+        try:
+            self.compiled = pipe.build(loop=(1, 1 + n_loop))
+        except _rt.NGB200Error as e:
+            if 'shared memory' in str(e):
+                raise ValueError(f'a block of {block} bodies does not fit one tile ({e}); use FusedStep') from e
+            raise
         # per-set operands never change between steps: resolved once
         self._static = {}
         for j, c in enumerate(self.sets):

@@ -511,6 +511,9 @@ def test_chain_step_partial_tiles_zero_pattern_and_validation():
                 g, r = getattr(got, f).numpy(), getattr(ref, f).numpy()
                 assert np.isfinite(g).all()
                 assert np.abs(g - r).max() <= (0 if not zeros else tol * 200) * max(1.0, np.abs(r).max()), (tdt, bpt, zeros, f)
-    scrambled = [type(bsets[0])(bsets[0].body_idx.flip(1), bsets[0].anchors, bsets[0].compliance), bsets[1]]
-    with pytest.raises(ValueError):
-        ChainStep(big, scrambled)
+    # 100 chains whose first colour set is listed in reverse: the only block that contains every constraint is the whole
+    # system (1200 bodies > the 1024 a tile can hold): refused, with a pointer to FusedStep
+    wide, wsets = replicate_chains(bodies, sets, 100)
+    scrambled = [type(wsets[0])(wsets[0].body_idx.flip(1), wsets[0].anchors, wsets[0].compliance), wsets[1]]
+    with pytest.raises(ValueError, match='FusedStep'):
+        ChainStep(wide, scrambled)
