@@ -905,6 +905,8 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        import hashlib
+        source_sha1 = hashlib.sha1(prog.source.encode()).hexdigest()[:16]       # staleness check of the cited ncu capture
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, 'profiles', 'r02_sandwich_traffic.json')
         if not os.path.exists(tp):
@@ -912,7 +914,7 @@ def run_ours(args):
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get('dram_bytes_per_launch'), {'file': os.path.relpath(tp, ROOT), 'commit': tj.get('commit'),
-                                                                      'kernel_source_hash': tj.get('kernel_source_hash')}
+                                                                      'kernel_source_sha1': tj.get('kernel_source_sha1')}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -924,7 +926,7 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': BYTES_PER_POINT * n, 'kernel_ms': ms,
-                         'kernel_source_hash': getattr(prog, 'source_hash', None)},
+                         'kernel_source_sha1': source_sha1, 'traffic_is_current': bool(traffic_src and traffic_src.get('kernel_source_sha1') == source_sha1)},
             'parity_ok_all_ranks': parity_ok_all, 'parity_err_max_over_ranks': perr_all, 'parity_tol': TOL['cfg2'],
             'parity_how': 'every rank: first and last 2^16 points of its slice, timed kernel vs oracle port on the host',
             'faithful_ms_per_step': faithful_ms,

@@ -444,8 +444,8 @@ class ChainStep:
                 raise ValueError('ChainStep(exploit_zeros=True) was specialised on the zero pattern of other inertia tables; '
                                  'build a new ChainStep for these bodies')
         n = bodies.motor.shape[0]
-        motor = ctx.mvtype(ctx, bodies.motor.subspace, soa_empty(8, (n,), ctx.dtype, ctx.device))
-        rate = ctx.mvtype(ctx, bodies.rate.subspace, soa_empty(6, (n,), ctx.dtype, ctx.device))
+        motor = ctx.mvtype(ctx, bodies.motor.subspace, soa_empty(len(bodies.motor.subspace), (n,), ctx.dtype, ctx.device))
+        rate = ctx.mvtype(ctx, bodies.rate.subspace, soa_empty(len(bodies.rate.subspace), (n,), ctx.dtype, ctx.device))
         arrays = dict(self._static, motor=bodies.motor, rate=bodies.rate, first_moment=bodies.first_moment,
                       inertia=bodies.inertia, inertia_inv=bodies.inertia_inv, damping=bodies.damping, gravity=bodies.gravity,
                       motor_out=motor, rate_out=rate)

@@ -17,6 +17,7 @@ def jobs():
     for k, (fn, params) in enumerate(T.GPU_MATRIX):
         out += [('identity', (k, descr)) for descr in params]
     out += [('identity_single', k) for k in range(len(T.GPU_SINGLES))]
+    out += [('physics_signature', d) for d in ('x+y+w0', 'x+y+z+', 'x+y+')]
     return out
 
 
@@ -37,6 +38,12 @@ def run_job(job):
             for mode in ('fast', 'faithful'):
                 ctx = ctx_of(pqr, dtype, mode)
                 _run(ctx, fn, [(getattr(ctx.subspace, s)(), 'batch' if k == 'batch' else 'single') for s, k in specs])
+    elif kind == 'physics_signature':
+        import test_physics as TP
+        try:
+            TP._chain_vs_generic(ctx_of(arg, torch.float64, 'fast'), arg, exact=False)
+        except AssertionError:
+            pass
     else:
         import test_reference_identities as T
         try:

@@ -191,6 +191,41 @@ def test_physics_replicated_chains_gpu():
         assert np.array_equal(gm, np.broadcast_to(gm[0], gm.shape))          # every chain follows the same arithmetic
 
 
+# ---- other signatures: the reference's chain demo runs in 2D elliptic space by default (run_chain_numpy.py:9-16) ------------
+def _chain_vs_generic(ctx, descr, exact):
+    from numga_b200.examples.physics import ChainStep, replicate_chains, setup_bodies
+    bodies, sets = setup_bodies(ctx, n_bodies=6, compliance=1e-2 if descr == 'x+y+' else 1e-9)
+    nb = bodies.rate.values.shape[-1]
+    bodies = bodies.copy(rate=bodies.rate + ctx.multivector.bivector(0.3 * np.random.default_rng(1).standard_normal((6, nb))))
+    ref = bodies.integrate(DT, sets).integrate(DT, sets)                 # written like the reference, one kernel per method
+    big, bsets = replicate_chains(bodies, sets, 3)
+    got = ChainStep(big, bsets, unroll=2, bodies_per_tile=12).integrate(big, DT)
+    for f in ('motor', 'rate'):
+        g = getattr(got, f).values.cpu().numpy().reshape(3, 6, -1)
+        r = getattr(ref, f).values.cpu().numpy()
+        assert np.isfinite(g).all()
+        if exact:
+            assert np.array_equal(g, np.broadcast_to(r, g.shape)), (descr, f)
+        else:
+            assert np.abs(g - r[None]).max() <= 1e-9 * max(1.0, np.abs(r).max()), (descr, f)
+
+
+@pytest.mark.parametrize('descr', ['x+y+w0', 'x+y+z+', 'x+y+'])
+def test_chain_step_in_other_signatures_cpu_emulated(descr):
+    """2D PGA, 3D elliptic and the reference demo's default 2D elliptic space: the chain-resident kernel equals the
+    reference-style `Body.integrate` (dimension- and signature-independent code, core.py docstring)."""
+    from cpu_emulation import emulate_launches, emulated_context
+    with emulate_launches():
+        _chain_vs_generic(emulated_context(descr, torch.float64), descr, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('descr', ['x+y+w0', 'x+y+z+', 'x+y+'])
+def test_chain_step_in_other_signatures_gpu(descr):
+    from numga_b200 import B200Context
+    _chain_vs_generic(B200Context(descr, dtype=torch.float64, device='cuda:0'), descr, exact=False)
+
+
 # ---- free tumbling (numga/examples/tennis_racket_theorem.py) ------------------------------------------------------------
 def _tennis(ctx, n):
     from numga_b200.examples.physics import Body
