@@ -143,6 +143,19 @@ static int current_device(int *dev_out, int want_device /* -1 = whatever is curr
     return NGB200_OK;
 }
 
+// Restores the calling thread's current context on scope exit (the host-buffer entry points take a device ordinal and
+// may have to make another device's primary context current while they run).
+struct CtxGuard {
+    CUcontext prev = nullptr;
+    bool armed = false;
+    CtxGuard() { if (g_drv.ok && g_drv.p_cuCtxGetCurrent(&prev) == CUDA_SUCCESS) armed = true; }
+    ~CtxGuard() {
+        if (!armed) return;
+        CUcontext now = nullptr;
+        if (g_drv.p_cuCtxGetCurrent(&now) == CUDA_SUCCESS && now != prev) g_drv.p_cuCtxSetCurrent(prev);
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // program object
 // ------------------------------------------------------------------------------------------
@@ -2232,6 +2245,7 @@ extern "C" int ngb200_program_run_host(ngb200_program *P, const ngb200_operand *
     if (P->n_params > 0 && !params) return fail(NGB200_ERR_INVALID, "program needs %d scalar params", P->n_params);
     int rc = need_driver();
     if (rc) return rc;
+    CtxGuard restore_context;
     int dev;
     rc = current_device(&dev, device);
     if (rc) return rc;
@@ -2306,6 +2320,7 @@ extern "C" int ngb200_host_copy_control(void *host_in, int64_t in_bytes, void *h
         return fail(NGB200_ERR_INVALID, "bad argument");
     int rc = need_driver();
     if (rc) return rc;
+    CtxGuard restore_context;
     int dev;
     rc = current_device(&dev, device);
     if (rc) return rc;
