@@ -662,33 +662,51 @@ def extra_configs(torch, B200Context, rank, peak):
     opt.disable()
     del bv
     out.append(training_step_config(torch, B200Context, rank, peak))
-    out.extend(generic_physics_configs(torch, B200Context, rank, peak))
+    out.extend(generic_physics_configs(torch, B200Context, rank, peak, modes=('eager',)))
     return out
 
 
-def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22, modes=('eager', 'lazy')):
-    """Supplementary: the rigid-body step written exactly like the reference (Body.integrate, one multivector method
-    after the other), run eagerly (one kernel per method) and with automatic fusion (B200Context(lazy=True))."""
+def generic_physics_configs(torch, B200Context, rank, peak, n_target=1 << 22, modes=('eager', 'lazy', 'lazy+graph')):
+    """The rigid-body step written exactly like the reference (Body.integrate, one multivector method after the other):
+    eagerly (one kernel per method), with automatic fusion (B200Context(lazy=True): 7 kernels per sub-step, host-bound by
+    the python recording), and with that lazy step captured ONCE into a CUDA graph (B200Context.capture) and replayed."""
     from numga_b200 import runtime as rt
     out = []
     n_chains = n_target // 12
     for mode in modes:
-        ctx = B200Context('x+y+z+w0', dtype=torch.float32, lazy=(mode == 'lazy'))
+        ctx = B200Context('x+y+z+w0', dtype=torch.float32, lazy=mode.startswith('lazy'))
         big, bsets = physics_state(ctx, n_chains, rank)
         big.rate.values
         state = [big]
 
-        def step():
-            new = state[0].integrate(PHYSICS_DT, bsets)
+        def advance(b):
+            new = b.integrate(PHYSICS_DT, bsets)
             new.motor.values, new.rate.values
-            state[0] = new
-        l0 = rt.launch_count()
-        step()
-        launches = rt.launch_count() - l0
+            return new
+        if mode == 'lazy+graph':
+            static = big.copy(motor=big.motor.copy(), rate=big.rate.copy())          # the graph's input buffers
+            graph = ctx.capture(advance, static)
+            launches = graph.n_kernels
+
+            def step():
+                new = graph.replay()
+                static.motor.values.copy_(new.motor.values)                           # feed the result back (2 small copies)
+                static.rate.values.copy_(new.rate.values)
+        else:
+            def step():
+                state[0] = advance(state[0])
+            l0 = rt.launch_count()
+            step()
+            launches = rt.launch_count() - l0
         ms = time_steps(step, 5, 2)
         n = 12 * n_chains
-        out.append({'id': 'extra', 'config': f'reference-style Body.integrate (unchanged formulas, {mode}: {launches} generated kernels per '
-                    f'sub-step), fp32, {n} bodies', 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'kernel_launches_per_step': launches})
+        label = {'eager': 'eager: one generated kernel per multivector method', 'lazy': 'lazy=True: automatic fusion, python recording every step',
+                 'lazy+graph': 'lazy=True captured once into a CUDA graph (ctx.capture) and replayed'}[mode]
+        out.append({'id': 'cfg5_reference_style', 'config': f'reference-style Body.integrate (unchanged formulas; {label}; {launches} generated kernels per '
+                    f'sub-step), fp32, {n} bodies', 'items': n, 'ms': ms, 'items_per_s': n / ms * 1e3, 'unit': 'body-steps/s',
+                    'kernel_launches_per_step': launches,
+                    'roofline': {'bound': 'hbm', 'bytes_per_item': 735.67, 'achieved': 735.67 * n / ms / 1e6, 'peak': peak, 'unit': 'GB/s',
+                                 'frac': 735.67 * n / ms / 1e6 / peak}})
         del big, bsets, state
         torch.cuda.empty_cache()
     return out
@@ -944,6 +962,7 @@ def run_ours(args):
         cfgs += run_cfg3(torch, B200Context, rank, peak)
         cfgs += run_cfg4(torch, B200Context, rank, peak)
         cfgs += run_cfg5(torch, B200Context, rank, peak)
+        cfgs += generic_physics_configs(torch, B200Context, rank, peak, modes=('lazy', 'lazy+graph'))
         if args.extra:
             cfgs += extra_configs(torch, B200Context, rank, peak)
         line['configs'] = cfgs
