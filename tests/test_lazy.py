@@ -177,3 +177,32 @@ def test_reference_identities_also_hold_under_lazy_fusion(which, monkeypatch):
     monkeypatch.setenv('NGB200_TEST_LAZY', '1')
     descr = {'test_bisect': (3, 0, 1), 'test_motor_split': (3, 0, 1), 'test_inverse_compare': (2, 1, 0), 'test_study': (4, 0, 1)}[which]
     getattr(T, which)(descr, 'cpu')
+
+
+@pytest.mark.gpu
+def test_lazy_physics_step_captured_into_a_cuda_graph():
+    """`ctx.capture` around the reference-style, lazily fused `Body.integrate`: the python recording runs once, every
+    replay is one driver call; results equal the un-captured lazy step, and follow in-place updates of the state."""
+    from numga_b200 import B200Context
+    from numga_b200.examples.physics import replicate_chains, setup_bodies
+    ctx = B200Context('x+y+z+w0', dtype=torch.float64, device='cuda:0', lazy=True)
+    bodies, sets = setup_bodies(ctx, n_bodies=12)
+    big, bsets = replicate_chains(bodies, sets, 50)
+    big = big.copy(rate=big.rate + ctx.multivector.bivector(0.3 * np.random.default_rng(4).standard_normal((600, 6))))
+    big.rate.values
+
+    def advance(b):
+        new = b.integrate(1 / 200, bsets)
+        new.motor.values, new.rate.values
+        return new
+    want1 = advance(big)
+    want2 = advance(want1)
+    static = big.copy(motor=big.motor.copy(), rate=big.rate.copy())
+    graph = ctx.capture(advance, static)
+    assert graph.n_kernels == 7
+    got1 = graph.replay()
+    assert torch.equal(got1.motor.values, want1.motor.values) and torch.equal(got1.rate.values, want1.rate.values)
+    static.motor.values.copy_(got1.motor.values)
+    static.rate.values.copy_(got1.rate.values)
+    got2 = graph.replay()
+    assert torch.equal(got2.motor.values, want2.motor.values) and torch.equal(got2.rate.values, want2.rate.values)
