@@ -9,6 +9,7 @@
 // C ABI of libnumga_b200.so (function pointers handed over at start-up; no link-time dependency).
 #include <ATen/ATen.h>
 #include <ATen/core/grad_mode.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
@@ -71,6 +72,7 @@ static py::object launch(FastPlan &p, const std::vector<at::Tensor> &inputs, con
             if (sz[d] != es[d] || (es[d] > 1 && st[d] != et[d])) return py::none();
         in_ptrs[k] = t.data_ptr();
     }
+    const c10::cuda::CUDAGuard device_guard((c10::DeviceIndex)p.device);   // the plan's device is current while we allocate and launch
     std::vector<at::Tensor> outs;
     outs.reserve(nout);
     const auto opts = at::TensorOptions().dtype(p.dtype).device(at::kCUDA, p.device);

@@ -161,6 +161,22 @@ class CompiledPipeline:
             assert domain < 0 or bs == 1 or _prod(v.shape[:-1]) == 1, f'{name}: not structure-of-arrays'
         return keep, ops
 
+    def _check_aliasing(self, tensors):
+        """Operands that no phase writes are read through the non-coherent path (`ld.global.nc`) by the kernel, which
+        is only valid if nothing else in the launch writes that memory: a written operand may not overlap a read-only one."""
+        written = {b[1] for _, _, _, outs in self.phases for b in outs if b[0] == rt.BIND_GLOBAL}
+        spans = []
+        for slot, t in enumerate(tensors):
+            st = t.untyped_storage()
+            spans.append((st.data_ptr(), st.data_ptr() + st.nbytes(), slot))
+        for lo, hi, slot in spans:
+            if slot not in written:
+                continue
+            for lo2, hi2, other in spans:
+                if other != slot and other not in written and lo < hi2 and lo2 < hi and hi > lo and hi2 > lo2:
+                    raise ValueError(f'pipeline output {self.pipe.globals[slot][0]!r} shares memory with the read-only operand '
+                                     f'{self.pipe.globals[other][0]!r}; pass a separate destination')
+
     def validate(self, arrays, items):
         """Bounds check of every index operand (the kernel itself does none): rows addressed in a shared buffer must
         fall inside the tile of the item that addresses them, rows addressed in a global array inside that array.  Done
@@ -199,6 +215,7 @@ class CompiledPipeline:
         counts = [int(items[d]) for d in pipe.domains]
         n_tiles = max(-(-c // ipt) for c, ipt in zip(counts, pipe.items_per_tile))
         keep, ops = self.operands(arrays)
+        self._check_aliasing(keep)
         if n_tiles > 0 and ctx.can_launch():
             self.program.launch(ops, counts, n_tiles, repeat, [float(p) for p in params], ctx.stream_handle())
         return keep

@@ -188,3 +188,18 @@ def test_pipeline_index_operands_are_bounds_checked_on_the_host():
         cp.launch(bad, {'node': 16, 'edge': 8})
     with pytest.raises(ValueError, match="'i0'"):
         cp.launch(dict(arrays, i0=torch.tensor([0, 1, 2, 3, 8, 9, 10, 16])), {'node': 16, 'edge': 8})
+
+
+def test_pipeline_refuses_an_output_that_aliases_a_read_only_operand():
+    from numga_b200 import B200Context
+    from numga_b200.pipeline import Pipeline
+    ctx = B200Context((3, 0, 1), device='cpu', compile_only=True)
+    S = ctx.subspace
+    pipe = Pipeline(ctx, {'node': 8})
+    a, out = pipe.array('a', S.vector(), 'node'), pipe.array('out', S.vector(), 'node')
+    pipe.phase('node', lambda x: x * 2, [a], [out])
+    cp = pipe.build()
+    x = ctx.multivector.vector(torch.zeros(16, 4))
+    cp.launch({'a': x, 'out': ctx.multivector.vector(torch.zeros(16, 4))}, {'node': 16})
+    with pytest.raises(ValueError, match='shares memory'):
+        cp.launch({'a': x, 'out': x}, {'node': 16})
