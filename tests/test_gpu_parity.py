@@ -476,6 +476,8 @@ def test_generated_gather_scatter_and_batch_sums_on_device(dtype):
     idx = torch.as_tensor(rng.integers(-5000, 5000, size=(3, 1111)), device='cuda')
     got = m[idx]
     assert got.shape == (3, 1111) and np.array_equal(got.numpy(), x[idx.cpu().numpy()])
+    host_idx = torch.as_tensor(rng.integers(0, 5000, size=(64,)))               # an index tensor living on the HOST is moved over
+    assert np.array_equal(m[host_idx].numpy(), x[host_idx.numpy()])
     perm = torch.as_tensor(rng.permutation(5000)[:777], device='cuda')
     rows = ctx.multivector.motor(rng.standard_normal((777, 8)).astype(dtype))
     new = m.at[perm].set(rows)
