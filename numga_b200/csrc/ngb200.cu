@@ -1630,6 +1630,7 @@ struct ngb200_pipeline {
     std::vector<PipePhase> phases;
     int loop_begin = 0, loop_end = 0, n_params = 0;
     int tpb = 128, minb = 1;
+    int warps = 1;                            // > 1: WARP TILES -- a tile is processed by ONE warp (tpb == 32), `warps` tiles per CTA, __syncwarp() barriers
     int n_value_globals = 0, n_index_globals = 0;
     size_t smem = 0, param_bytes = 0;
     std::vector<size_t> soff;                 // element offset of every shared buffer (component-major layout)
@@ -1679,7 +1680,8 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                     g.remat[j] = g.n_remat++;
     }
     max_need += total_nu * (f64 ? 2 : 1);
-    int minb = 65536 / (Q.tpb * (max_need > 32 ? max_need : 32));
+    const int cta_threads = Q.tpb * Q.warps;
+    int minb = 65536 / (cta_threads * (max_need > 32 ? max_need : 32));
     Q.minb = minb < 1 ? 1 : (minb > 8 ? 8 : minb);
     if (env_int("NGB200_PIPE_MINB", 0) > 0) Q.minb = env_int("NGB200_PIPE_MINB", 0);
     gens[0]->emit_prelude(s, 1, env_int("NGB200_LDMODE", 0), env_int("NGB200_STMODE", 0), false);
@@ -1698,12 +1700,22 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         gens[k]->emit_body(s, &nl);
         Q.n_live += nl;
     }
-    if (Q.minb > 1 && 65536 / (Q.tpb * Q.minb) < 255) appendf(s, "extern \"C\" __global__ void __launch_bounds__(NGB_TPB, %d) ngb_pipeline(const PParams p) {\n", Q.minb);
-    else s += "extern \"C\" __global__ void __launch_bounds__(NGB_TPB) ngb_pipeline(const PParams p) {\n";
-    s += "  extern __shared__ __align__(16) unsigned char ngb_raw[];\n  T* const sm = reinterpret_cast<T*>(ngb_raw);\n";
+    if (Q.minb > 1 && 65536 / (cta_threads * Q.minb) < 255) appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) ngb_pipeline(const PParams p) {\n", cta_threads, Q.minb);
+    else appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d) ngb_pipeline(const PParams p) {\n", cta_threads);
+    s += "  extern __shared__ __align__(16) unsigned char ngb_raw[];\n";
+    if (Q.warps > 1) {
+        // warp tiles: every warp of the CTA owns its own tile and its own slice of shared memory; nothing is shared between
+        // warps, so the phase barriers are __syncwarp() and warps never wait for each other
+        appendf(s, "  const int ngb_tid = threadIdx.x & 31;\n  T* const sm = reinterpret_cast<T*>(ngb_raw) + (threadIdx.x >> 5) * %zuLL;\n", Q.smem / esize(Q.dtype) / Q.warps);
+    } else {
+        s += "  const int ngb_tid = threadIdx.x;\n  T* const sm = reinterpret_cast<T*>(ngb_raw);\n";
+    }
     for (size_t k = 0; k < Q.phases.size(); ++k)
         appendf(s, "  T u%zu[%d]; ngb_uniform_%zu(p, u%zu);\n", k, gens[k]->NU > 0 ? gens[k]->NU : 1, k, k);
-    s += "  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {\n";
+    if (Q.warps > 1)
+        appendf(s, "  for (long long tile = (long long)blockIdx.x * %d + (threadIdx.x >> 5); tile < p.n_tiles; tile += (long long)gridDim.x * %d) {\n", Q.warps, Q.warps);
+    else
+        s += "  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {\n";
     // Global operands that no phase writes are read through the non-coherent path (`ld.global.nc`): besides the cache
     // path, it tells ptxas the data cannot change under the kernel, so loads are scheduled next to their uses
     // (ChainStep fp32: 168 -> 128 registers, +1 % / +3 % at ten / one sub-steps per launch).
@@ -1716,8 +1728,8 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         Gen &g = *gens[k];
         const int d = ph.domain, ipt = Q.ipt[d];
         appendf(s, "%s{ // phase %zu: domain %d, %d items per tile\n", ind, k, d, ipt);
-        if (ipt <= Q.tpb) appendf(s, "%s  const int i = threadIdx.x;\n%s  if (i < %d) {\n", ind, ind, ipt);
-        else appendf(s, "%s  for (int i = threadIdx.x; i < %d; i += NGB_TPB) {\n", ind, ipt);
+        if (ipt <= Q.tpb) appendf(s, "%s  const int i = ngb_tid;\n%s  if (i < %d) {\n", ind, ind, ipt);
+        else appendf(s, "%s  for (int i = ngb_tid; i < %d; i += NGB_TPB) {\n", ind, ipt);
         appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    if (gi < p.n[%d]) {\n", ind, ipt, ind, d);
         appendf(s, "%s      T x[%d]; T y[%d];\n", ind, g.NX > 0 ? g.NX : 1, g.NY > 0 ? g.NY : 1);
         // row of an indexed access: global arrays use the index value itself, shared buffers the tile-local part
@@ -1834,7 +1846,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         };
         const bool elide = next >= 0 && Q.phases[next].domain == ph.domain && direct_only(ph) && direct_only(Q.phases[next]) &&
                            env_int("NGB200_PIPE_ELIDE", 1);
-        if (!elide) appendf(s, "%s__syncthreads();\n", ind);
+        if (!elide) appendf(s, "%s%s;\n", ind, Q.warps > 1 ? "__syncwarp()" : "__syncthreads()");
     };
     // L2 prefetch of what the LATER phases of this tile read from global memory (per-item constants and tables that are
     // not parked in shared memory): issued before the first phase, so that their DRAM latency overlaps the load phase
@@ -1862,7 +1874,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             const int d = kv.first, ipt = Q.ipt[d];
             // one prefetch per 32-byte sector: every 8th (fp32) / 4th (fp64) item of a row issues it
             const int per = 32 / es;
-            appendf(s, "    for (int i = threadIdx.x * %d; i < %d; i += NGB_TPB * %d) {\n", per, ipt, per);
+            appendf(s, "    for (int i = ngb_tid * %d; i < %d; i += NGB_TPB * %d) {\n", per, ipt, per);
             appendf(s, "      const long long gi = tile * %dLL + i;\n      if (gi < p.n[%d]) {\n", ipt, d);
             for (auto &sc : kv.second)
                 appendf(s, "        asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p.g[%d].ptr + %dLL * p.g[%d].cs + gi));\n",
@@ -1938,6 +1950,12 @@ extern "C" int ngb200_pipeline_create(const ngb200_pipeline_desc *d, ngb200_pipe
     if (Q->smem > 227 * 1024) return fail(NGB200_ERR_INVALID, "tile needs %zu bytes of shared memory (limit 232448)", Q->smem);
     Q->tpb = d->threads_per_tile > 0 ? d->threads_per_tile : std::min(256, (max_ipt + 31) / 32 * 32);
     if (Q->tpb % 32 || Q->tpb > 1024) return fail(NGB200_ERR_INVALID, "threads per tile must be a multiple of 32, at most 1024");
+    if (Q->tpb == 32) {                                        // one warp per tile: several tiles per CTA (see pipeline_source)
+        Q->warps = env_int("NGB200_PIPE_WARPS", 8);
+        if (Q->warps < 1) Q->warps = 1;
+        while (Q->warps > 1 && Q->smem * Q->warps > 227 * 1024) Q->warps /= 2;
+        Q->smem = (Q->smem + 15) / 16 * 16 * Q->warps;
+    }
     Q->param_bytes = 16 * (size_t)std::max(1, Q->n_value_globals) + 8 * (size_t)std::max(1, Q->n_index_globals) +
                      8 * (size_t)std::max(1, Q->n_params) + 8 * Q->ipt.size() + 8 + 8;
     if (Q->param_bytes > 4000) return fail(NGB200_ERR_INVALID, "too many operands for one kernel");
@@ -2099,7 +2117,7 @@ extern "C" int ngb200_pipeline_launch(ngb200_pipeline *Q, const ngb200_operand *
             if (Q->smem > 48 * 1024) CU(cuFuncSetAttribute(L.f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)Q->smem));
             int sms = 0, nb = 0;
             CU(cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
-            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.f, Q->tpb, Q->smem));
+            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, L.f, Q->tpb * Q->warps, Q->smem));
             L.grid = sms * (nb > 0 ? nb : 1);
             L.ready.store(1, std::memory_order_release);
         }
@@ -2129,9 +2147,9 @@ extern "C" int ngb200_pipeline_launch(ngb200_pipeline *Q, const ngb200_operand *
     w += 8;
     int rp = repeat;
     memcpy(w, &rp, 4);
-    const int64_t blocks = std::min<int64_t>(n_tiles, L.grid);
+    const int64_t blocks = std::min<int64_t>((n_tiles + Q->warps - 1) / Q->warps, L.grid);
     void *args[] = {buf};
-    CU(cuLaunchKernel(L.f, (unsigned)blocks, 1, 1, (unsigned)Q->tpb, 1, 1, (unsigned)Q->smem, (CUstream)stream, args, nullptr));
+    CU(cuLaunchKernel(L.f, (unsigned)blocks, 1, 1, (unsigned)(Q->tpb * Q->warps), 1, 1, (unsigned)Q->smem, (CUstream)stream, args, nullptr));
     g_launches.fetch_add(1);
     return NGB200_OK;
 }

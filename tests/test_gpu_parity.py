@@ -507,7 +507,7 @@ def test_chain_step_partial_tiles_zero_pattern_and_validation():
         big = big.copy(rate=big.rate + ctx.multivector.bivector(0.3 * np.random.default_rng(2).standard_normal((540, 6))))
         fs = FusedStep(big, bsets)
         ref = fs.integrate(fs.integrate(big, 1 / 200), 1 / 200)
-        for bpt, zeros in ((None, False), (84, False), (None, True)):
+        for bpt, zeros in ((None, False), (84, False), (60, False), (None, True)):       # 60 bodies per tile = one WARP per tile
             got = ChainStep(big, bsets, unroll=2, bodies_per_tile=bpt, exploit_zeros=zeros).integrate(big, 1 / 200)
             for f in ('motor', 'rate'):
                 g, r = getattr(got, f).numpy(), getattr(ref, f).numpy()
