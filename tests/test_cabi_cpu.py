@@ -182,6 +182,10 @@ def test_pipeline_c_abi_compiles_and_validates():
     assert 'float4' in src                      # 128-bit shared accesses
     with pytest.raises(rt.NGB200Error, match='no CPU fallback|CUDA'):
         p.launch([(1, 1, 1)] * 4, [64, 63], 1)
+    # tiles that need only one warp: several tiles per CTA, each warp with its own shared-memory slice, warp barriers
+    w = rt.PipelineProgram(rt.F32, rt.FAST, [32, 31], globals_, [(1, 0)], phases, (0, 0), 0)
+    assert '__syncwarp()' in w.source and '__syncthreads()' not in w.source and '(threadIdx.x >> 5)' in w.source
+    assert w.info['threads_per_tile'] == 32 and w.info['shared_bytes'] == 8 * ((32 + 4 + 1) * 16)
     bad = [(scale, 0, [(I, 0, -1)], [(S, 0, -1)]), (diff, 1, [(S, 0, -1), (S, 0, 2)], [(I, 3, -1)])]
     with pytest.raises(rt.NGB200Error, match='another domain'):
         rt.PipelineProgram(rt.F32, rt.FAST, [64, 63], globals_, [(1, 0)], bad, (0, 0), 0)
