@@ -451,3 +451,28 @@ class ChainStep:
                       motor_out=motor, rate_out=rate)
         self.compiled.launch(arrays, self._items, repeat=self.unroll, params=[dt])
         return bodies.copy(motor=motor, rate=rate)
+
+
+_STEPPERS = {}
+
+
+def step(bodies, constraint_sets, dt, unroll=10):
+    """`unroll` sub-steps of `dt / unroll` in ONE launch: the main-loop step of the reference's chain demo
+    (numga/examples/physics/run_chain_numpy.py:26-30).  Uses the chain-resident kernel when the system has block
+    structure (`ChainStep`), else the six-kernel arrangement (`FusedStep`) sub-step by sub-step.  The stepper is built
+    once per (context, constraint sets, unroll) and re-used."""
+    ctx = bodies.motor.context
+    key = (id(ctx), tuple(id(c) for c in constraint_sets), int(unroll), bodies.motor.shape[0])
+    entry = _STEPPERS.get(key)
+    if entry is None:
+        try:
+            stepper = ChainStep(bodies, constraint_sets, unroll=unroll)
+        except ValueError:
+            stepper = FusedStep(bodies, constraint_sets)
+        entry = _STEPPERS[key] = (stepper, ctx, tuple(constraint_sets))       # (keeps the keyed objects alive)
+    stepper = entry[0]
+    if isinstance(stepper, ChainStep):
+        return stepper.integrate(bodies, dt / unroll)
+    for _ in range(unroll):
+        bodies = stepper.integrate(bodies, dt / unroll)
+    return bodies

@@ -143,6 +143,11 @@ def test_physics_generic_and_fused_step_cpu_emulated():
         other.inertia_inv = big.inertia_inv.at[0, 0, 0].set(1.0)
         with pytest.raises(ValueError):
             cz.integrate(other, DT)
+        # `step` = the reference demo's main-loop step (run_chain_numpy.py:26-30): unroll sub-steps of dt / unroll
+        from numga_b200.examples.physics import step
+        stepped = step(bodies, sets, 2 * DT, unroll=2)
+        assert np.array_equal(stepped.motor.values.numpy(), two.motor.values.numpy())
+        assert np.array_equal(stepped.rate.values.numpy(), two.rate.values.numpy())
         with pytest.raises(ValueError):                           # a system without block structure is refused
             from numga_b200.examples.physics import _block_structure
             _block_structure(12, [torch.tensor([[0, 5], [11, 6]])], max_block=6)
