@@ -6,8 +6,9 @@ DAG is turned into ONE generated kernel when the data is needed: on access to `.
 reductions, passing the object to a non-lazy consumer ...), through `context.realize(a, b, ...)` (several results in
 one kernel), or when the pending DAG exceeds `context.lazy_limit` operations.  This is what `context.jit(fn)` does for
 an explicitly wrapped function, applied to ordinary eager-looking code: the reference's rigid-body step written
-exactly like numga/examples/physics/core.py (174 array passes there) runs as SEVEN kernels per sub-step
-(measured: 22.6 ms eagerly -> 2.9 ms at 4.2 M bodies; the hand-arranged FusedStep takes 1.07 ms).
+exactly like numga/examples/physics/core.py (174 array passes there) runs as SEVEN fused kernels per sub-step plus the
+four row copies its `.at[].set` calls imply (measured: 20.3 ms eagerly -> 2.7 ms at 4.2 M bodies, 1.74 ms when the step is
+captured into a CUDA graph with `context.capture`; the hand-arranged FusedStep takes 1.07 ms, ChainStep 0.64 ms).
 
 Gathers `x[idx]` (integer index arrays) and scatters `x.at[idx].set(y)` become index operands of the consuming /
 producing kernel; `x[j]` and `x.sum(axis=0)` over a small leading batch axis stay symbolic; a batch `[k, c]` whose
