@@ -324,7 +324,8 @@ class ChainStep:
     Needs the block structure `replicate_chains` produces (independent chains laid out one after the other); the
     formulas are the same traced python bodies `FusedStep` uses.  `integrate(bodies, dt)` = `unroll` sub-steps of dt."""
 
-    def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0, exploit_zeros=False):
+    def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0, exploit_zeros=False,
+                 recompute_maps=None):
         from numga_b200.pipeline import Pipeline, compact_operator, expand_operator
         from numga_b200.backend import _OperatorKey, kernel_space
         import torch
@@ -402,6 +403,16 @@ class ChainStep:
             s0, s1 = FusedStep._distribute(m0 << direction, m1 << direction, magnitude, inv0, inv1, compliance * 0)
             return r0 + s0, r1 + s1
 
+        # `Constraint.anchors_map` (rates -> velocity line at the anchor, base.py:147) is `anchors.inertia_map()`: 24
+        # quadratic forms of the 4 anchor coordinates.  The reference tabulates it once because every numpy pass is
+        # expensive; here re-evaluating it in registers (~150 flops per constraint and sub-step) is cheaper than
+        # streaming 2 x 24 table words per constraint through HBM / L2 every sub-step (29 % of the step's bytes).
+        # The arithmetic is the one that produced the table, so results do not change.
+        self.recompute_maps = (not self.exploit_zeros) if recompute_maps is None else bool(recompute_maps)
+
+        def v_apply_from_anchors(m0, m1, r0, r1, inv0, inv1, a0, a1, compliance, dt):
+            return v_apply(m0, m1, r0, r1, inv0, inv1, a0.inertia_map(), a1.inertia_map(), compliance, dt)
+
         per_set = []
         for j, c in enumerate(self.sets):
             i0, i1 = pipe.index(f'set{j}/i0', f'set{j}'), pipe.index(f'set{j}/i1', f'set{j}')
@@ -414,8 +425,12 @@ class ChainStep:
             pipe.phase(f'set{j}', apply, [s_motor[i0], s_motor[i1], s_inv[i0], s_inv[i1], a0, a1, comp, dt], [s_motor[i0], s_motor[i1]])
         pipe.phase('body', post, [s_motor, s_old, dt], [s_motor, s_rate])
         for j, (i0, i1, a0, a1, m0, m1, comp) in enumerate(per_set):
-            pipe.phase(f'set{j}', v_apply, [s_motor[i0], s_motor[i1], s_rate[i0], s_rate[i1], s_inv[i0], s_inv[i1], m0, m1, comp, dt],
-                       [s_rate[i0], s_rate[i1]])
+            if self.recompute_maps:
+                pipe.phase(f'set{j}', v_apply_from_anchors,
+                           [s_motor[i0], s_motor[i1], s_rate[i0], s_rate[i1], s_inv[i0], s_inv[i1], a0, a1, comp, dt], [s_rate[i0], s_rate[i1]])
+            else:
+                pipe.phase(f'set{j}', v_apply, [s_motor[i0], s_motor[i1], s_rate[i0], s_rate[i1], s_inv[i0], s_inv[i1], m0, m1, comp, dt],
+                           [s_rate[i0], s_rate[i1]])
         n_loop = 2 + 2 * len(self.sets)
         pipe.phase('body', lambda m, r: (m, r), [s_motor, s_rate], [o_motor, o_rate])
         from numga_b200 import runtime as _rt
