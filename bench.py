@@ -628,6 +628,17 @@ def run_cfg5(torch, B200Context, rank, peak, n_target=1 << 24, unroll=10, faithf
                           f'{u} sub-step(s) per launch', n_bodies * u, ms, state_once / u, peak, unit='body-steps/s',
                           parity_ok=parity[label]['ok'], parity=parity[label], kernel_launches_per_step=launches,
                           sub_steps_per_launch=u, bodies=n_bodies)
+                e['roofline']['dram_bytes_per_body_ncu'] = issue.get(f"cfg5_{tag}_dram_bytes_per_body") if not zeros else None
+                e['anchor_maps'] = ('re-evaluated in registers from the anchors (ChainStep(recompute_maps=True), the default) instead of '
+                                    'streaming the 2 x 24-word tables per constraint' if cs.recompute_maps else 'streamed from the tabulated anchors_map')
+                moved = e['roofline']['dram_bytes_per_body_ncu']
+                if moved and u == 1:
+                    # what this kernel really moves (ncu, profiles/r02_chain_*_final_ncu_full.csv): fewer bytes than SURVEY's
+                    # state-once figure, because the anchor maps are not read and 12 inertia entries are structurally dead
+                    e['roofline']['hbm_frac_of_bytes_moved'] = moved * n_bodies / ms / 1e6 / peak
+                    e['roofline']['note'] = ('frac is quoted on SURVEY 8d\'s 735.7 B/body as the contract asks; the kernel moves only '
+                                             'dram_bytes_per_body_ncu, so HBM is ~half busy and the kernel is bound by issue slots / latency '
+                                             '(issue_slot_utilisation_ncu), not by HBM')
                 if not zeros:
                     e['roofline']['issue_slot_utilisation_ncu'] = issue.get(f"cfg5_{tag}_{'one_substep' if u == 1 else 'ten_substeps'}_per_launch")
                     if u > 1:

@@ -1729,7 +1729,16 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         const int d = ph.domain, ipt = Q.ipt[d];
         appendf(s, "%s{ // phase %zu: domain %d, %d items per tile\n", ind, k, d, ipt);
         if (ipt <= Q.tpb) appendf(s, "%s  const int i = ngb_tid;\n%s  if (i < %d) {\n", ind, ind, ipt);
-        else appendf(s, "%s  for (int i = ngb_tid; i < %d; i += NGB_TPB) {\n", ind, ipt);
+        else {
+            // several items per thread: copy phases (no arithmetic: tile load / store) are unrolled so that the global
+            // loads of ALL of a thread's items are in flight together -- one DRAM round trip per phase instead of one per
+            // item (NGB200_PIPE_UNROLL: 0 never, 1 copy phases (default), 2 every phase)
+            const int mode = env_int("NGB200_PIPE_UNROLL", 1);
+            size_t arith = 0;
+            for (const ngb200_instr &I : ph.prog->instr) if (I.op != NGB200_OP_INPUT) ++arith;
+            if ((mode == 1 && arith == 0 && ipt <= 4 * Q.tpb) || mode >= 2) appendf(s, "%s  #pragma unroll\n", ind);
+            appendf(s, "%s  for (int i = ngb_tid; i < %d; i += NGB_TPB) {\n", ind, ipt);
+        }
         appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    if (gi < p.n[%d]) {\n", ind, ipt, ind, d);
         appendf(s, "%s      T x[%d]; T y[%d];\n", ind, g.NX > 0 ? g.NX : 1, g.NY > 0 ? g.NY : 1);
         // row of an indexed access: global arrays use the index value itself, shared buffers the tile-local part
