@@ -33,7 +33,9 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/numga_b200.h"
@@ -1700,6 +1702,45 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         gens[k]->emit_body(s, &nl);
         Q.n_live += nl;
     }
+    // NGB200_PIPE_PREFETCH=2: while a tile computes, the rows the NEXT tile of this CTA will read from global memory are
+    // pulled into L2 with one bulk prefetch per (array, component) row (cp.async.bulk.prefetch.L2: rows are contiguous per
+    // tile in the SoA layout), so the next load phase finds them in L2 and DRAM works during the compute phases.
+    struct PfRow { int kind, slot, comp, dom; };
+    std::vector<PfRow> pf_rows;
+    if (env_int("NGB200_PIPE_PREFETCH", 0) == 2) {
+        std::set<std::tuple<int, int, int, int>> seen;
+        for (size_t k = 0; k < Q.phases.size(); ++k) {
+            PipePhase &ph = Q.phases[k];
+            Gen &g = *gens[k];
+            std::vector<char> used(g.NX > 0 ? g.NX : 1, 0);
+            for (size_t v = 0; v < ph.prog->instr.size(); ++v) {
+                const ngb200_instr &I = ph.prog->instr[v];
+                if (I.op == NGB200_OP_INPUT && g.live[v] && !g.uniform[v]) used[g.xoff[I.a] + I.b] = 1;
+            }
+            for (size_t j = 0; j < ph.in.size(); ++j) {
+                const ngb200_bind &b = ph.in[j];
+                if (b.index >= 0) seen.insert(std::make_tuple(1, Q.gslot[b.index], 0, ph.domain));
+                if (b.kind != NGB200_BIND_GLOBAL || b.index >= 0 || ph.prog->in_mode[j] == NGB200_BROADCAST) continue;
+                for (int c = 0; c < ph.prog->in_width[j]; ++c)
+                    if (used[g.xoff[j] + c]) seen.insert(std::make_tuple(0, Q.gslot[b.slot], c, ph.domain));
+            }
+            for (const ngb200_bind &b : ph.out)
+                if (b.index >= 0) seen.insert(std::make_tuple(1, Q.gslot[b.index], 0, ph.domain));
+        }
+        for (auto &t : seen) pf_rows.push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t)});
+        if (!pf_rows.empty()) {
+            const char *names[4] = {"kind", "slot", "comp", "dom"};
+            for (int f = 0; f < 4; ++f) {
+                appendf(s, "__constant__ unsigned char ngb_pf_%s[%zu] = {", names[f], pf_rows.size());
+                for (size_t r = 0; r < pf_rows.size(); ++r)
+                    appendf(s, "%s%d", r ? "," : "", f == 0 ? pf_rows[r].kind : f == 1 ? pf_rows[r].slot : f == 2 ? pf_rows[r].comp : pf_rows[r].dom);
+                s += "};\n";
+            }
+            appendf(s, "__constant__ int ngb_pf_ipt[%zu] = {", Q.ipt.size());
+            for (size_t d = 0; d < Q.ipt.size(); ++d) appendf(s, "%s%d", d ? "," : "", Q.ipt[d]);
+            s += "};\n";
+        }
+    }
     if (Q.minb > 1 && 65536 / (cta_threads * Q.minb) < 255) appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) ngb_pipeline(const PParams p) {\n", cta_threads, Q.minb);
     else appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d) ngb_pipeline(const PParams p) {\n", cta_threads);
     s += "  extern __shared__ __align__(16) unsigned char ngb_raw[];\n";
@@ -1860,7 +1901,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
     // L2 prefetch of what the LATER phases of this tile read from global memory (per-item constants and tables that are
     // not parked in shared memory): issued before the first phase, so that their DRAM latency overlaps the load phase
     // and the first compute phases instead of being exposed at the head of every later phase.
-    if (env_int("NGB200_PIPE_PREFETCH", 0)) {     // measured on B200: 5.41 vs 5.77 G body-steps/s with it on (profiles/r02_chain_sweep.txt): off
+    if (env_int("NGB200_PIPE_PREFETCH", 0) == 1) {     // measured on B200: 5.41 vs 5.77 G body-steps/s with it on (profiles/r02_chain_sweep.txt): off
         std::map<std::pair<int, int>, int> seen;        // (global slot, component) -> domain
         for (size_t k = 1; k < Q.phases.size(); ++k) {
             PipePhase &ph = Q.phases[k];
@@ -1891,7 +1932,24 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             s += "      }\n    }\n";
         }
     }
-    for (int k = 0; k < Q.loop_begin; ++k) emit_phase(k, "    ");
+    auto emit_next_tile_prefetch = [&]() {
+        if (pf_rows.empty()) return;
+        if (Q.warps > 1) appendf(s, "    { const long long nt = tile + (long long)gridDim.x * %d;\n", Q.warps);
+        else s += "    { const long long nt = tile + gridDim.x;\n";
+        appendf(s, "      if (nt < p.n_tiles) for (int r = ngb_tid; r < %zu; r += NGB_TPB) {\n", pf_rows.size());
+        s += "        const int d = ngb_pf_dom[r], sl = ngb_pf_slot[r];\n"
+             "        const long long start = nt * ngb_pf_ipt[d];\n"
+             "        long long cnt = p.n[d] - start; if (cnt > ngb_pf_ipt[d]) cnt = ngb_pf_ipt[d];\n"
+             "        const char* a; long long bytes;\n"
+             "        if (ngb_pf_kind[r]) { a = (const char*)(p.idx[sl] + start); bytes = cnt * 8; }\n"
+             "        else { a = (const char*)(p.g[sl].ptr + (long long)ngb_pf_comp[r] * p.g[sl].cs + start); bytes = cnt * (long long)sizeof(T); }\n"
+             "        const unsigned head = (unsigned)((16 - ((unsigned long long)a & 15)) & 15);\n"
+             "        a += head; bytes = (bytes - head) & ~15LL;\n"
+             "        if (bytes > 0) asm volatile(\"cp.async.bulk.prefetch.L2.global [%0], %1;\" :: \"l\"(a), \"r\"((unsigned)bytes) : \"memory\");\n"
+             "      }\n    }\n";
+    };
+    for (int k = 0; k < Q.loop_begin; ++k) { emit_phase(k, "    "); if (k == 0) emit_next_tile_prefetch(); }
+    if (Q.loop_begin == 0) emit_next_tile_prefetch();
     if (Q.loop_end > Q.loop_begin) {
         s += "    for (int rep = 0; rep < p.repeat; ++rep) {\n";
         for (int k = Q.loop_begin; k < Q.loop_end; ++k) emit_phase(k, "      ");
