@@ -636,7 +636,7 @@ def run_cfg5(torch, B200Context, rank, peak, n_target=1 << 24, unroll=10, faithf
                     # what this kernel really moves (ncu, profiles/r02_chain_*_final_ncu_full.csv): fewer bytes than SURVEY's
                     # state-once figure, because the anchor maps are not read and 12 inertia entries are structurally dead
                     e['roofline']['hbm_frac_of_bytes_moved'] = moved * n_bodies / ms / 1e6 / peak
-                    e['roofline']['note'] = ('frac is quoted on SURVEY 8d\'s 735.7 B/body as the contract asks; the kernel moves only '
+                    e['roofline']['note'] = (f'frac is quoted on SURVEY 8d\'s {state_once:.1f} B/body as the contract asks; the kernel moves only '
                                              'dram_bytes_per_body_ncu, so HBM is ~half busy and the kernel is bound by issue slots / latency '
                                              '(issue_slot_utilisation_ncu), not by HBM')
                 if not zeros:
