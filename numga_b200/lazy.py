@@ -7,8 +7,8 @@ reductions, passing the object to a non-lazy consumer ...), through `context.rea
 one kernel), or when the pending DAG exceeds `context.lazy_limit` operations.  This is what `context.jit(fn)` does for
 an explicitly wrapped function, applied to ordinary eager-looking code: the reference's rigid-body step written
 exactly like numga/examples/physics/core.py (174 array passes there) runs as SEVEN fused kernels per sub-step plus the
-four row copies its `.at[].set` calls imply (measured: 20.3 ms eagerly -> 2.7 ms at 4.2 M bodies, 1.74 ms when the step is
-captured into a CUDA graph with `context.capture`; the hand-arranged FusedStep takes 1.07 ms, ChainStep 0.64 ms).
+four row copies its `.at[].set` calls imply (measured: 20.3 ms eagerly -> 2.7 ms at 4.2 M bodies, 1.59 ms when the step is
+captured into a CUDA graph with `context.capture`; the hand-arranged FusedStep takes 1.07 ms, ChainStep 0.56 ms).
 
 Gathers `x[idx]` (integer index arrays) and scatters `x.at[idx].set(y)` become index operands of the consuming /
 producing kernel; `x[j]` and `x.sum(axis=0)` over a small leading batch axis stay symbolic; a batch `[k, c]` whose
@@ -306,7 +306,9 @@ class LazyEngine:
     def realize(self, targets, out=None):
         """Compute all pending `targets` (LazyMultiVectors) with ONE kernel.  Pending intermediates of the DAG that are
         still referenced from outside it (a python variable, another pending expression) are written by the same
-        kernel, so nothing is computed twice later; intermediates only the DAG knows stay in registers."""
+        kernel, so nothing is computed twice later; intermediates only the DAG knows stay in registers.  Exception:
+        values marked `_remat` (bound-operator kernels much wider than their sources, `B200Operator.partial`) are never
+        written -- re-evaluating them in every consumer moves fewer bytes than reading a table would."""
         targets = [t for t in targets if isinstance(t, self.cls) and t._values is None]
         for t in [t for t in targets if t._node.key == 'gather']:      # a bare gather asked for its values: torch does it
             from numga_b200.backend import as_soa
@@ -373,7 +375,7 @@ class LazyEngine:
         # references to an intermediate beyond those of the DAG itself mean somebody will ask for it again
         extra = [] if out is not None else \
             [mv for mv, n in _outside_references(inner, dag_refs)
-             if n > 0 and id(mv) not in target_ids and mv.shape == bshape]
+             if n > 0 and id(mv) not in target_ids and mv.shape == bshape and not getattr(mv, '_remat', False)]
         results = targets + extra
         outs = tuple(index[id(t._node)] for t in results)
         structure = (tuple(order), outs)

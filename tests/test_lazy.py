@@ -91,6 +91,34 @@ def test_shared_intermediates_are_kept_dead_ones_are_not(where):
 
 
 @pytest.mark.parametrize('where', WHERE)
+def test_wide_bound_operators_are_re_evaluated_not_tabulated(where):
+    """`points.inertia_map()` (numga/multivector/multivector.py:385-395; tabulated once per constraint set by the
+    reference, examples/physics/core.py:133) under lazy=True: binding launches nothing, applying the map is ONE kernel
+    that reads the 4-word points and the rates but no 36-entry table, and the map stays symbolic for the next use; a
+    narrow map (a motor's 4x4 sandwich matrix from 8 words) is tabulated by the first kernel that uses it."""
+    rng = np.random.default_rng(5)
+    with _contexts((3, 0, 1), where) as (eager, lazy, counter):
+        pts, rates = rng.standard_normal((7, 4)), rng.standard_normal((7, 6))
+        want = _np(eager.multivector.antivector(pts).inertia_map()(eager.multivector.bivector(rates)))
+        counter['n'] = 0
+        imap = lazy.multivector.antivector(pts).inertia_map()
+        assert counter['n'] == 0 and imap.shape == (7,)
+        for k in range(2):                       # (a repeated call takes the C++ fast path, which `counter` does not see)
+            got = imap(lazy.multivector.bivector(rates))
+            got.values
+            assert counter['n'] in (1, k + 1) and imap._flat is None and imap._lazy.pending
+        assert sorted(len(s) for s in list(lazy.engine.cache.values())[-1].in_subspaces) == [4, 6]
+        assert np.abs(_np(got) - want).max() <= 1e-14 * np.abs(want).max()
+        assert np.array_equal(imap.kernel.cpu().numpy(), eager.multivector.antivector(pts).inertia_map().kernel.cpu().numpy())
+        assert not imap._lazy.pending                                    # asking for the table computes it, once
+        motors = lazy.multivector.motor(rng.standard_normal((7, 8)))
+        smap = motors.sandwich_map()
+        out = smap(lazy.multivector.vector(rng.standard_normal((7, 4))))
+        out.values
+        assert not smap._lazy.pending                                    # narrow map: written by the kernel that used it
+
+
+@pytest.mark.parametrize('where', WHERE)
 def test_reference_style_physics_step_fuses_automatically(where):
     """Body.integrate written like numga/examples/physics/core.py: ~170 kernels eagerly, 11 when lazy, same
     states as the unmodified reference."""
