@@ -492,6 +492,26 @@ def run_cfg3(torch, B200Context, rank, peak, faithful=True):
         e['roofline']['compute_bound'] = True
         e['roofline']['issue_slot_utilisation_ncu'] = issue.get('cfg3_' + tag)
         out.append(e)
+        # supplementary: the same round trip with the opt-in closed forms (numga_b200.optimized: the reference's optional
+        # extension/optimized.py for exp / normalized, plus the inverse of its exp as the logarithm) -- one HBM-bound kernel
+        import numga_b200.optimized as opt
+        opt.enable()
+        try:
+            g = c.jit(lambda x: x.exp().normalized().motor_log())
+            got_c = g(c.multivector.bivector(hb.astype(npd))).numpy()
+            ms_c = time_steps(lambda: g(bv), 5, 3)
+            n_c = max(v.program.info['n_instr'] for k, v in c.engine.cache.items() if k[0][0] == 'jit')
+        finally:
+            opt.disable()
+        tol_c = 1e-5 if tag == 'f32' else 1e-12
+        ec = entry('cfg3_' + tag + '_closed_form', f'config 3 (supplementary): the same round trip with the OPT-IN closed forms of '
+                   f'numga_b200.optimized (3D PGA only), {tag}, batch 2^28, one kernel', n, ms_c, ub, peak, flops_per_item=n_c,
+                   parity_ok=bool(rel_err(got_c, want64) <= tol_c), parity_err_vs_fp64=rel_err(got_c, want64),
+                   reference_err_vs_fp64=e_ref, parity_tol=tol_c)
+        ec['note'] = ('not the default dispatch: closed forms replace the reference\'s bisection algorithms (its own optional '
+                      'extension/optimized.py does so for exp / normalized; the logarithm is the inverse of that exp); gated against '
+                      'the fp64 oracle, where it is MORE accurate than the reference\'s same-precision bisection (reference_err_vs_fp64)')
+        out.append(ec)
         del bv
         torch.cuda.empty_cache()
     return out

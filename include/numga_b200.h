@@ -88,6 +88,7 @@ enum ngb200_opcode {
     NGB200_OP_MIN = 18,
     NGB200_OP_MAX = 19,
     NGB200_OP_SELECT_GT0 = 20, /* a > 0 ? b : c                                   */
+    NGB200_OP_ATAN2 = 21, /* atan2(a, b): angle of the point (b, a)               */
     NGB200_OP_COUNT_
 };
 

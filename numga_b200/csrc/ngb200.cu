@@ -344,6 +344,7 @@ struct Gen {
             case NGB200_OP_MIN: return std::string("fmin") + sfx + "(" + a + ", " + b + ")";
             case NGB200_OP_MAX: return std::string("fmax") + sfx + "(" + a + ", " + b + ")";
             case NGB200_OP_SELECT_GT0: return "(" + a + " > T(0) ? " + b + " : " + c + ")";
+            case NGB200_OP_ATAN2: return std::string("atan2") + sfx + "(" + a + ", " + b + ")";
         }
         return "T(0)";
     }
@@ -437,6 +438,7 @@ struct Gen {
             case NGB200_OP_MIN: return both("fminf($a, $b)");
             case NGB200_OP_MAX: return both("fmaxf($a, $b)");
             case NGB200_OP_SELECT_GT0: return both("($a > 0.0f ? $b : $c)");
+            case NGB200_OP_ATAN2: return both("atan2f($a, $b)");
         }
         return "ngb_dup(0.0f)";
     }

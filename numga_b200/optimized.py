@@ -1,4 +1,4 @@
-"""Opt-in closed forms for 3D PGA (signature +++0): `normalized` of motors and `exp` of bivectors.
+"""Opt-in closed forms for 3D PGA (signature +++0): `normalized` of motors, `exp` of bivectors, `motor_log` of motors.
 
 Mirrors the reference's OPTIONAL `numga/multivector/extension/optimized.py` (not imported or active by default there
 either): the default dispatch keeps the generic, signature-agnostic algorithms (bisection exp: ~570 instructions per
@@ -10,13 +10,18 @@ on traced values, so each still becomes ONE generated kernel and fuses with what
     opt.enable()        # registers at position 0 of the `normalized` / `exp` dispatch, like the reference
     opt.disable()       # removes them again
 
+`motor_log` has no closed form in the reference (its log is the 16-square-root bisection, logexp.py:101-117); the one
+here is the exact inverse of the reference's closed-form `exp` above (principal branch, rotation angle in [0, pi]), so
+that the whole exp -> normalized -> motor_log round trip of BASELINE config 3 becomes ONE HBM-bound kernel when the
+closed forms are enabled.  It is checked against the bisection logarithm in fp64 (tests/test_optimized.py).
+
 One deliberate difference: the reference's full-bivector `exp` computes `t = m (c - s) / l` and returns nan for a
 bivector without rotation part (l = 0); here that limit is taken (t = -m / 3 as l -> 0).
 """
 import numpy as np
 
 from numga_b200 import runtime as rt
-from numga_b200.extension import exp, normalized
+from numga_b200.extension import exp, motor_log, normalized
 from numga_b200.trace import SymArray
 
 _MOTOR = (0, 3, 5, 6, 9, 10, 12, 15)          # 1, xy, xz, yz, xw, yw, zw, xyzw
@@ -90,6 +95,29 @@ def exp_bivector(b):
     return _pack(b.context, b.context.subspace.motor(), out)
 
 
+def log_motor(M):
+    """Bivector b with exp(b) = M for a NORMALIZED 3D PGA motor: the inverse of `exp_bivector`.
+    With L = XY^2 + XZ^2 + YZ^2 = sin^2 a:  a = atan2(sqrt L, e);  1/s = a / sin a;  m = P / s;
+    t = m (cos a - s) / a^2;  rotation part = (XY, XZ, YZ) / s;  translation part = ((XW, YW, ZW) -+ t (yz, xz, xy)) / s."""
+    e, XY, XZ, YZ, XW, YW, ZW, P = _parts(M.values)
+    t_ = e.trace
+    L = XY * XY + XZ * XZ + YZ * YZ
+    sL = L ** 0.5
+    a = SymArray(t_, [t_.atan2(sL.regs[0], e.regs[0])])
+    # 1 / s = a / sin a, -> 1 as the rotation vanishes
+    rs = SymArray(t_, [t_.select_gt0(t_.sub(sL.regs[0], t_.const(1e-20)), t_.div(a.regs[0], sL.regs[0]), t_.const(1.0))])
+    xy, xz, yz = XY * rs, XZ * rs, YZ * rs
+    m = P * rs
+    l = a * a
+    s = SymArray(t_, [t_.select_gt0(t_.sub(sL.regs[0], t_.const(1e-20)), t_.div(sL.regs[0], a.regs[0]), t_.const(1.0))])
+    # (cos a - sin a / a) / a^2 = -1/3 + a^2/30 - a^4/840 + ...: the series where the difference would cancel
+    series = t_.add(t_.const(-1.0 / 3.0), t_.mul(l.regs[0], t_.sub(t_.const(1.0 / 30.0), t_.mul(l.regs[0], t_.const(1.0 / 840.0)))))
+    ratio = t_.select_gt0(t_.sub(l.regs[0], t_.const(0.01)), t_.div(t_.sub(e.regs[0], s.regs[0]), l.regs[0]), series)
+    t = m * SymArray(t_, [ratio])
+    out = [xy, xz, yz, (XW - t * yz) * rs, (YW + t * xz) * rs, (ZW - t * xy) * rs]
+    return _pack(M.context, M.context.subspace.bivector(), out)
+
+
 _REGISTERED = []
 
 
@@ -101,7 +129,8 @@ def enable():
             (normalized, lambda s: _is_3dpga(s, _MOTOR), normalize_3dpga_motor),
             (exp, lambda s: _is_3dpga(s, _TRANS), exp_degenerate_bivector),
             (exp, lambda s: _is_3dpga(s, _ROT), exp_nondegenerate_bivector),
-            (exp, lambda s: _is_3dpga(s, _BIVECTOR), exp_bivector)):
+            (exp, lambda s: _is_3dpga(s, _BIVECTOR), exp_bivector),
+            (motor_log, lambda s: _is_3dpga(s, _MOTOR), log_motor)):
         dispatch.register(cond, position=0)(fn)
         _REGISTERED.append((dispatch, fn))
     _invalidate()

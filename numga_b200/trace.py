@@ -201,6 +201,10 @@ class Trace:
     def nan_to_num(self, a, nan):
         return self._emit(rt.OP_NAN_TO_NUM, a, self.const(nan))
 
+    def atan2(self, y, x):
+        f = self._fold(np.arctan2, y, x)
+        return f if f is not None else self._emit(rt.OP_ATAN2, y, x)
+
     def select_gt0(self, cond, a, b):
         """cond > 0 ? a : b"""
         if a == b:
@@ -573,7 +577,7 @@ def build_vjp(ir, np_dtype, faithful=False, wanted=None):
         elif op == rt.OP_ABS: v = t.abs(new[a])
         elif op == rt.OP_NAN_TO_NUM: v = t._emit(op, new[a], new[b])
         elif op in (rt.OP_FMA, rt.OP_SELECT_GT0): v = t._emit(op, new[a], new[b], new[c])
-        elif op in (rt.OP_MIN, rt.OP_MAX): v = t._emit(op, new[a], new[b])
+        elif op in (rt.OP_MIN, rt.OP_MAX, rt.OP_ATAN2): v = t._emit(op, new[a], new[b])
         else: v = t._emit(op, new[a])          # exp, log, sin, cos
         new.append(v)
     # reverse sweep
@@ -634,6 +638,9 @@ def build_vjp(ir, np_dtype, faithful=False, wanted=None):
             acc(a, t._emit(rt.OP_SELECT_GT0, d, g, zero)); acc(b, t._emit(rt.OP_SELECT_GT0, d, zero, g))
         elif op == rt.OP_SELECT_GT0:
             acc(b, t._emit(rt.OP_SELECT_GT0, a, g, zero)); acc(c, t._emit(rt.OP_SELECT_GT0, a, zero, g))
+        elif op == rt.OP_ATAN2:               # d atan2(y, x) = (x dy - y dx) / (x^2 + y^2)
+            w = t.div(g, t.add(t.mul(a, a), t.mul(b, b)))
+            acc(a, t.mul(w, b)); acc(b, t.neg(t.mul(w, a)))
         else:
             raise NotImplementedError(f'derivative of opcode {op}')
     wanted = range(len(in_regs)) if wanted is None else wanted      # only these inputs' cotangents are produced

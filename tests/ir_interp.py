@@ -43,6 +43,7 @@ def run_ir(ir, inputs, dtype, params=()):
             elif op == rt.OP_MIN: v = np.minimum(vals[a], vals[b])
             elif op == rt.OP_MAX: v = np.maximum(vals[a], vals[b])
             elif op == rt.OP_SELECT_GT0: v = np.where(vals[a] > 0, vals[b], vals[c])
+            elif op == rt.OP_ATAN2: v = np.arctan2(vals[a], vals[b])
             else: raise ValueError(op)
             vals.append(np.asarray(v, dtype=dtype))
     outs = [np.zeros((batch, w), dtype=dtype) for w in ir['out_width']]

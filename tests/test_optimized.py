@@ -77,6 +77,48 @@ def test_closed_form_exp_is_one_small_kernel_and_handles_pure_translations(where
         assert n_closed < 60 < 400 < n_generic
 
 
+@pytest.mark.parametrize('where', WHERE)
+def test_closed_form_motor_log_equals_the_bisection_logarithm(where, optimized):
+    """`log_motor` (ours; the reference's log is the bisection, logexp.py:101-117) against `motor_log_bisect` in fp64 and
+    as the inverse of the closed-form exp: general motors, pure rotors, pure translators, the identity, a tiny angle."""
+    rng = np.random.RandomState(3)
+    with _context(where) as ga:
+        B = ga.subspace.bivector()
+        b = random_subspace(ga, B, (200,), rng) * 0.5
+        special = np.zeros((5, 6))
+        special[0, :3] = [0.3, -0.2, 0.9]              # pure rotation
+        special[1, 3:] = [1.0, 2.0, -3.0]              # pure translation
+        special[3] = [1e-9, 0, 0, 0.5, 0.25, -1.0]     # rotation angle below every threshold
+        special[4] = [2e-2, 1e-2, -3e-2, 0.5, 0.25, -1.0]   # inside the series branch
+        b = b.concatenate(ga.multivector(B, special), axis=0)
+        m = b.exp_bisect().normalized()
+        want = values_of(m.motor_log_bisect())
+        optimized.enable()
+        got = values_of(m.motor_log())
+        f = ga.jit(lambda x: x.exp().normalized().motor_log())
+        back = values_of(f(b))
+        n_closed = len([c for k, c in ga.engine.cache.items() if k[0][0] == 'jit'][0].ir['instr'])
+        optimized.disable()
+        assert np.abs(got - want).max() < 1e-8 and np.abs(got - values_of(b)).max() < 1e-8
+        assert np.abs(back - values_of(b)).max() < 1e-12          # closed-form round trip, one kernel
+        assert n_closed < 250
+
+
+@pytest.mark.parametrize('where', WHERE)
+def test_gradient_of_the_closed_form_logarithm(where, optimized):
+    """atan2 (the one opcode the logarithm adds) differentiates: d/db |log(exp(b))|^2 = 2 b."""
+    rng = np.random.RandomState(4)
+    with _context(where) as ga:
+        if where != 'gpu':
+            pytest.skip('autograd runs the VJP kernel on the device')
+        optimized.enable()
+        v = torch.tensor(0.4 * rng.randn(16, 6), device='cuda:0', dtype=torch.float64, requires_grad=True)
+        b = ga.multivector(ga.subspace.bivector(), v)
+        out = ga.jit(lambda x: x.exp().normalized().motor_log())(b)
+        (out.values ** 2).sum().backward()
+        assert torch.allclose(v.grad, 2 * v.detach(), atol=1e-9)
+
+
 def test_enable_disable_leave_other_algebras_alone(optimized):
     from numga_b200 import B200Context
     optimized.enable()
