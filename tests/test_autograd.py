@@ -159,6 +159,24 @@ def test_vjp_of_ir_with_duplicate_values_and_abs_at_zero():
     assert t.grad.tolist() == gx.reshape(-1).tolist()
 
 
+def test_vjp_of_atan2_matches_torch():
+    """The ATAN2 opcode (closed-form motor logarithm, numga_b200/optimized.py) and its adjoint, all four quadrants."""
+    from ir_interp import run_ir
+    from numga_b200 import runtime as rt
+    from numga_b200.trace import build_vjp
+    ir = dict(in_width=[1, 1], in_mode=[rt.VARYING, rt.VARYING], out_width=[1], n_params=0, consts=[],
+              instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_INPUT, 1, 0, 0), (rt.OP_ATAN2, 0, 1, 0)], stores=[(0, 0, 2)])
+    y, x = np.array([[0.5], [0.5], [-2.0], [-2.0]]), np.array([[1.5], [-1.5], [0.25], [-0.25]])
+    g = np.array([[1.0], [2.0], [3.0], [4.0]])
+    (out,) = run_ir(ir, [y, x], np.float64)
+    gy, gx = run_ir(build_vjp(ir, np.float64), [y, x, g], np.float64)
+    ty, tx = torch.tensor(y, requires_grad=True), torch.tensor(x, requires_grad=True)
+    tout = torch.atan2(ty, tx)
+    tout.backward(torch.tensor(g))
+    assert np.allclose(out, tout.detach().numpy(), rtol=1e-15)
+    assert np.allclose(gy, ty.grad.numpy(), rtol=1e-14) and np.allclose(gx, tx.grad.numpy(), rtol=1e-14)
+
+
 @pytest.mark.parametrize('where', WHERE)
 def test_torch_compile_fullgraph_motor_fitting(where):
     """`ctx.torch_op`: generated programs registered as `torch.library.custom_op`s (fake kernels from the IR's output

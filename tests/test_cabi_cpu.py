@@ -146,6 +146,7 @@ int main(void) {
            offsetof(ngb200_program_desc, stores), offsetof(ngb200_program_desc, vec));
     printf("%zu %zu\\n", sizeof(ngb200_program_info), offsetof(ngb200_program_info, cubin_bytes));
     printf("%d %d %d %d %d\\n", NGB200_VARYING, NGB200_BROADCAST, NGB200_INDEXED, NGB200_REDUCED, NGB200_TILED);
+    printf("%d %d %d %d %d\\n", NGB200_OP_INPUT, NGB200_OP_FMA, NGB200_OP_SELECT_GT0, NGB200_OP_ATAN2, NGB200_OP_COUNT_);
     return 0;
 }
 ''')
@@ -159,6 +160,22 @@ int main(void) {
     assert lines[1].split() == [str(x) for x in (ctypes.sizeof(d), d.consts.offset, d.stores.offset, d.vec.offset)]
     assert lines[2].split() == [str(ctypes.sizeof(rt.ProgramInfo)), str(rt.ProgramInfo.cubin_bytes.offset)]
     assert lines[3].split() == [str(x) for x in (rt.VARYING, rt.BROADCAST, rt.INDEXED, rt.REDUCED, rt.TILED)]
+    assert lines[4].split() == [str(x) for x in (rt.OP_INPUT, rt.OP_FMA, rt.OP_SELECT_GT0, rt.OP_ATAN2, rt.OP_ATAN2 + 1)]
+
+
+def test_every_opcode_generates_code_in_both_precisions():
+    """One program per arithmetic opcode of include/numga_b200.h (compile only, no GPU): the generator knows them all,
+    in the scalar and in the packed (two items per thread) emitters."""
+    ops = [getattr(rt, n) for n in dir(rt) if n.startswith('OP_') and n not in ('OP_INPUT', 'OP_CONST', 'OP_PARAM')]
+    assert len(ops) == rt.OP_ATAN2 + 1 - 3
+    for dtype in (rt.F32, rt.F64):
+        for op in ops:
+            n = rt.N_OPERANDS.get(op, 2)
+            instr = [(rt.OP_INPUT, 0, k, 0) for k in range(3)] + [(op, 0, 1 if n > 1 else 0, 2 if n > 2 else 0)]
+            mode = rt.FAST if op == rt.OP_FMA else rt.FAITHFUL
+            for m in {mode, rt.FAST}:
+                prog = rt.Program.from_ir(dtype, m, [3], [rt.VARYING], [1], [rt.VARYING], 0, [], instr, [(0, 0, 3)])
+                assert prog.info['cubin_bytes'] > 0, (op, dtype, m)
 
 
 def test_pipeline_c_abi_compiles_and_validates():
