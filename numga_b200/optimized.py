@@ -148,7 +148,7 @@ def _invalidate():
     """Compiled-function caches are keyed on the method name, not on the dispatch table: drop them in every live
     context (the reference does the same with `mv.exp.cache = {}`, optimized.py:52,129)."""
     from numga_b200.backend import B200Context
-    for ctx in list(B200Context.instances):
+    for ctx in list(B200Context.instances or ()):          # (None until the first context exists)
         ctx.engine.cache.clear()
         ctx.engine.fast_cache.clear()
         ctx.lazy_engine.signatures.clear()

@@ -20,6 +20,12 @@ elif which == 'cga':
     ctx = B200Context((4, 1, 0)); F = ctx.subspace.full()
     a, b = device_mv(ctx, F, 1 << 24, 5, 0), device_mv(ctx, F, 1 << 24, 6, 0)
     run = lambda: a * b
+elif which in ('roundtrip_closed', 'roundtrip_closed64'):
+    import numga_b200.optimized as opt
+    opt.enable()                      # opt-in closed forms: exp / normalized (reference's optimized.py) + log_motor
+    ctx = B200Context((3, 0, 1), dtype=torch.float64 if which.endswith('64') else torch.float32)
+    bv = device_mv(ctx, ctx.subspace.bivector(), 1 << 26, 7, 0, scale=0.5)
+    f = ctx.jit(lambda x: x.exp().normalized().motor_log()); run = lambda: f(bv)
 elif which in ('roundtrip', 'roundtrip64'):
     ctx = B200Context((3, 0, 1), dtype=torch.float64 if which.endswith('64') else torch.float32)
     bv = device_mv(ctx, ctx.subspace.bivector(), 1 << 24, 7, 0, scale=0.5)

@@ -119,6 +119,17 @@ def test_gradient_of_the_closed_form_logarithm(where, optimized):
         assert torch.allclose(v.grad, 2 * v.detach(), atol=1e-9)
 
 
+def test_enable_before_any_context_exists():
+    """`opt.enable()` as the first statement of a program (no context yet: nothing to invalidate) must not raise."""
+    import subprocess
+    import sys
+    code = ("import numga_b200.optimized as opt; opt.enable(); from numga_b200 import B200Context; "
+            "c = B200Context((3, 0, 1), device='cpu', compile_only=True); opt.disable(); print('ok')")
+    root = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
+
+
 def test_enable_disable_leave_other_algebras_alone(optimized):
     from numga_b200 import B200Context
     optimized.enable()
