@@ -16,14 +16,14 @@ class B200Context(AbstractContext):
     backend's einsum).  `engine` is the numga_b200 context that owns kernels, caches and the tracer; numga objects
     are mapped onto it by blade set (the integer tables of both are identical, tests/test_tables_golden.py)."""
 
-    def __init__(self, algebra, otype=B200Operator, dtype=torch.float32, device='cuda:0', mode='fast', engine=None):
+    def __init__(self, algebra, otype=B200Operator, dtype=torch.float32, device='cuda:0', mode='fast', engine=None, lazy=False):
         if dtype in (np.float32, np.float64, 'float32', 'float64'):
             dtype = {np.float32: torch.float32, np.float64: torch.float64, 'float32': torch.float32, 'float64': torch.float64}[dtype]
         super().__init__(algebra=algebra, otype=otype, dtype=dtype, mvtype=B200MultiVector)
         self.device = torch.device(device)
         self.mode = mode
         d = self.algebra.description
-        self.engine = engine or numga_b200.B200Context(d.description_str, dtype=dtype, device=device, mode=mode)
+        self.engine = engine or numga_b200.B200Context(d.description_str, dtype=dtype, device=device, mode=mode, lazy=lazy)
         assert tuple(self.engine.algebra.description.pqr) == tuple(d.pqr)
         self._to_engine, self._from_engine = {}, {}
 
@@ -48,10 +48,15 @@ class B200Context(AbstractContext):
             return s
 
     def to_engine(self, mv):
-        return self.engine.mvtype(self.engine, self.engine_subspace(mv.subspace), mv.values)
+        if mv._emv is not None:                   # came from the engine (possibly still a recorded expression)
+            return mv._emv
+        mv._emv = self.engine.mvtype(self.engine, self.engine_subspace(mv.subspace), mv.values)
+        return mv._emv
 
     def from_engine(self, emv):
-        return B200MultiVector(self, self.numga_subspace(emv.subspace), emv.values)
+        if getattr(emv, 'pending', False):        # lazy engine: nothing computed yet, keep the recorded expression
+            return B200MultiVector(self, self.numga_subspace(emv.subspace), None, emv)
+        return B200MultiVector(self, self.numga_subspace(emv.subspace), emv.values, emv)
 
     # ---- arrays (plumbing) --------------------------------------------------------------------------------------------
     def coerce_array(self, values, dtype=None):

@@ -20,7 +20,23 @@ from numga_b200.multivector import COMPUTE_METHODS, EXTENSION_METHODS
 
 
 class B200MultiVector(AbstractMultiVector):
-    values: torch.Tensor
+    """`values` is a property: with a lazy engine (`B200Context(..., lazy=True)`) a result is first only the RECORDED
+    expression held by the engine multivector `_emv`; asking for `values` (or anything that needs them) computes the
+    whole pending chain with one generated kernel (numga_b200/lazy.py)."""
+
+    def __init__(self, context, subspace, values=None, engine_mv=None):
+        self.context, self.subspace = context, subspace
+        self._values, self._emv = values, engine_mv
+
+    @property
+    def values(self) -> torch.Tensor:
+        if self._values is None:
+            self._values = self._emv.values
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values, self._emv = v, None
 
     @classmethod
     def construct(cls, context, values, subspace):
@@ -37,13 +53,35 @@ class B200MultiVector(AbstractMultiVector):
 
     # ---- data movement (torch = plumbing; results go back to structure-of-arrays) -----------------------------------
     def __getitem__(self, idx):
+        ctx = self.context
+        if ctx.engine.lazy:                      # gathers / slices stay part of the recorded expression
+            return ctx.from_engine(ctx.to_engine(self)[idx])
         if isinstance(idx, np.ndarray):
             idx = torch.as_tensor(idx, device=self.values.device)
         return self.copy(values=as_soa(self.values[idx]))
 
     @property
     def shape(self):
-        return tuple(self.values.shape[:-1])
+        return tuple(self._emv.shape) if self._values is None else tuple(self._values.shape[:-1])
+
+    @property
+    def at(self):
+        """`mv.at[idx].set(rows)` (numga/multivector/helper.py): with a lazy engine the kernel that computes `rows` writes
+        them straight into the copy; otherwise numga's generic helper (`context.set_array`)."""
+        ctx = self.context
+        if not ctx.engine.lazy:
+            return AbstractMultiVector.at.fget(self)
+        this = self
+
+        class _At:
+            def __getitem__(self, idx):
+                class _Set:
+                    def set(self, rows):
+                        if isinstance(rows, B200MultiVector):
+                            rows = ctx.to_engine(rows)
+                        return ctx.from_engine(ctx.to_engine(this).at[idx].set(rows))
+                return _Set()
+        return _At()
 
     def __len__(self):
         return self.shape[0]

@@ -18,12 +18,31 @@ from numga_b200 import backend as E
 from numga_b200.operator import Operator as EngineOperator
 
 
+class _PendingKernel:
+    """Stands in for the float kernel of a bound operator that a lazy engine has only recorded (row gathers
+    `inertia_inv[idx]`, wide maps that are re-evaluated by their consumers): the shape is known, anything else computes
+    the kernel."""
+
+    def __init__(self, eop):
+        self._eop = eop
+
+    @property
+    def shape(self):
+        return tuple(self._eop.shape) + tuple(self._eop.kshape)
+
+    def __getattr__(self, name):
+        return getattr(self._eop.kernel, name)
+
+    def __getitem__(self, idx):
+        return self._eop.kernel[idx]
+
+
 class B200Operator(AbstractConcreteOperator):
 
     # ---- engine counterparts ------------------------------------------------------------------------------------------
     @property
     def is_dense(self):
-        return isinstance(self.operator.kernel, torch.Tensor)
+        return isinstance(self.operator.kernel, (torch.Tensor, _PendingKernel))
 
     def _engine_axes(self):
         return tuple(self.context.engine_subspace(a) for a in self.operator.axes)
@@ -48,7 +67,7 @@ class B200Operator(AbstractConcreteOperator):
         """numga operator around an engine dense operator (float kernel [*batch, n_in.., n_out])."""
         ctx = self.context
         axes = tuple(ctx.numga_subspace(a) for a in eop.axes)
-        out = type(self)(ctx, Operator(eop.kernel, axes))
+        out = type(self)(ctx, Operator(_PendingKernel(eop) if eop._flat is None else eop.kernel, axes))
         out.__dict__['_engine_op'] = eop
         out.__dict__['_mask'] = eop.mask
         return out

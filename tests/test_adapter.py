@@ -43,6 +43,7 @@ def _emulated_factory(A, dtype=torch.float64):
         from numga.algebra.algebra import Algebra
         alg = algebra if isinstance(algebra, Algebra) else Algebra(algebra)
         engine = emulated_context(alg.description.description_str, torch.float64, mode='faithful')
+        engine.lazy = bool(kw.get('lazy', False))
         return A.B200Context(alg, dtype=torch.float64, device='cpu', mode='faithful', engine=engine)
     return make
 
@@ -128,3 +129,39 @@ def test_reference_physics_example_runs_unchanged_on_the_adapter():
         new = bodies.integrate(1 / 200, sets)
         assert np.abs(new.motor.values.numpy() - G['f64/step1/motor']).max() < 1e-12
         assert np.abs(new.rate.values.numpy() - G['f64/step1/rate']).max() < 1e-10 * np.abs(G['f64/step1/rate']).max()
+
+
+@needs_reference
+def test_reference_physics_example_fuses_automatically_on_the_lazy_adapter():
+    """The SAME unmodified reference files on `B200Context(..., lazy=True)`: multivector methods and operator calls are
+    only recorded, `bodies.motor[idx]` / `inertia_inv[idx]` gathers and `.at[idx].set` scatters join the recorded
+    expressions, and one sub-step of `Body.integrate` (numga/examples/physics/core.py:80-88; 174 array passes on the numpy
+    backend) runs as a dozen generated kernels with the same result."""
+    A = _load_adapter()
+    from numga.examples.physics.setup_chain import setup_bodies
+    from cpu_emulation import emulate_launches
+    from numga_b200 import backend as B
+    G = np.load(os.path.join(HERE, 'golden', 'physics.npz'))
+    counter, launches = {'n': 0}, {}
+    with emulate_launches():
+        orig = B.CompiledFunction.launch               # (the emulated launch)
+
+        def counting(self, *a, **k):
+            counter['n'] += 1
+            return orig(self, *a, **k)
+        B.CompiledFunction.launch = counting
+        try:
+            for lazy in (False, True):
+                ga = _emulated_factory(A)('x+y+z+w0', lazy=lazy)
+                bodies, sets = setup_bodies(ga, n_bodies=12)
+                bodies = bodies.copy(rate=ga.multivector.bivector(G['f64/start/rate']))
+                bodies.rate.values, bodies.motor.values
+                counter['n'] = 0
+                new = bodies.integrate(1 / 200, sets)
+                m, r = new.motor.values.numpy(), new.rate.values.numpy()
+                launches[lazy] = counter['n']
+                assert np.abs(m - G['f64/step1/motor']).max() < 1e-12
+                assert np.abs(r - G['f64/step1/rate']).max() < 1e-10 * np.abs(G['f64/step1/rate']).max()
+        finally:
+            B.CompiledFunction.launch = orig
+    assert launches[True] <= 16 < 100 < launches[False], launches
