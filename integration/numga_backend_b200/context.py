@@ -96,6 +96,18 @@ class B200Context(AbstractContext):
     def logical_xor(self, x, y): return torch.logical_xor(x, y)
     def logical_or(self, x, y): return torch.logical_or(x, y)
 
+    def capture(self, fn, *args, warmup=1):
+        """Record every kernel `fn(*args)` launches into one CUDA graph and return it (`graph.replay()`, `graph.result`):
+        numga_b200 `B200Context.capture`.  `fn` works on this backend's multivectors; with `lazy=True` it must ask for
+        the `values` of what it returns, so that the recorded expressions are launched inside the capture."""
+        return self.engine.capture(fn, *args, warmup=warmup)
+
+    def realize(self, *mvs):
+        """Compute the pending expressions of several multivectors with ONE kernel (lazy engine); no-op otherwise."""
+        if self.engine.lazy:
+            self.engine.realize(*[self.to_engine(m) for m in mvs])
+        return mvs
+
     # ---- fusion of user code: the whole function becomes ONE kernel -------------------------------------------------
     def jit(self, fn):
         """`fn(*multivectors_or_python_scalars) -> multivector(s)`, written against the numga multivector API, compiled

@@ -158,6 +158,7 @@ def test_reference_physics_example_fuses_automatically_on_the_lazy_adapter():
                 bodies.rate.values, bodies.motor.values
                 counter['n'] = 0
                 new = bodies.integrate(1 / 200, sets)
+                ga.realize(new.motor, new.rate)
                 m, r = new.motor.values.numpy(), new.rate.values.numpy()
                 launches[lazy] = counter['n']
                 assert np.abs(m - G['f64/step1/motor']).max() < 1e-12
