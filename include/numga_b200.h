@@ -89,6 +89,8 @@ enum ngb200_opcode {
     NGB200_OP_MAX = 19,
     NGB200_OP_SELECT_GT0 = 20, /* a > 0 ? b : c                                   */
     NGB200_OP_ATAN2 = 21, /* atan2(a, b): angle of the point (b, a)               */
+    NGB200_OP_PARTNER = 22, /* value a as held by the thread of item i ^ 1 (warp shuffle): PIPELINE PHASES ONLY, items come in
+                               pairs (2k, 2k + 1), e.g. the two sides of a constraint (numga/examples/physics/core.py arrays [2, c]) */
     NGB200_OP_COUNT_
 };
 

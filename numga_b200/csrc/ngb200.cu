@@ -244,7 +244,7 @@ static int n_operands_of(int op) {
     switch (op) {
         case NGB200_OP_INPUT: case NGB200_OP_CONST: case NGB200_OP_PARAM: return 0;
         case NGB200_OP_NEG: case NGB200_OP_SQRT: case NGB200_OP_RSQRT: case NGB200_OP_RCP: case NGB200_OP_ABS:
-        case NGB200_OP_EXP: case NGB200_OP_LOG: case NGB200_OP_SIN: case NGB200_OP_COS: return 1;
+        case NGB200_OP_EXP: case NGB200_OP_LOG: case NGB200_OP_SIN: case NGB200_OP_COS: case NGB200_OP_PARTNER: return 1;
         case NGB200_OP_FMA: case NGB200_OP_SELECT_GT0: return 3;
         default: return 2;
     }
@@ -273,6 +273,7 @@ struct Gen {
     // in fp64: the registers they would occupy for the whole phase are worth more than the extra LDS); value = slot in xp[]
     std::vector<int> remat;
     int n_remat = 0;
+    bool has_partner = false;     // the program exchanges values between the threads of an item pair (pipeline phases only)
 
     explicit Gen(const ngb200_program &p)
         : P(p), f64(p.dtype == NGB200_F64), faithful(p.flags & NGB200_FAITHFUL) {
@@ -345,6 +346,7 @@ struct Gen {
             case NGB200_OP_MAX: return std::string("fmax") + sfx + "(" + a + ", " + b + ")";
             case NGB200_OP_SELECT_GT0: return "(" + a + " > T(0) ? " + b + " : " + c + ")";
             case NGB200_OP_ATAN2: return std::string("atan2") + sfx + "(" + a + ", " + b + ")";
+            case NGB200_OP_PARTNER: return "__shfl_xor_sync(0xffffffffu, " + a + ", 1)";
         }
         return "T(0)";
     }
@@ -452,6 +454,7 @@ struct Gen {
         for (int v = 0; v < n; ++v) {
             const ngb200_instr &I = P.instr[v];
             if (I.op < 0 || I.op >= NGB200_OP_COUNT_) return fail(NGB200_ERR_INVALID, "instr %d: bad opcode %d", v, I.op);
+            if (I.op == NGB200_OP_PARTNER) has_partner = true;
             int k = n_operands_of(I.op);
             const int ops[3] = {I.a, I.b, I.c};
             for (int j = 0; j < k; ++j)
@@ -989,6 +992,7 @@ static int finish_program(ngb200_program *P, int vec_hint) {
     Gen gen(*P);
     int rc = gen.analyse();
     if (rc) return rc;
+    if (gen.has_partner) return fail(NGB200_ERR_INVALID, "NGB200_OP_PARTNER is only available in pipeline phases (items must map to adjacent lanes)");
     int live_guess = 0;
     for (char c : gen.live) live_guess += c;
     // items per thread: small programs are HBM-bound -> 128-bit accesses (4 x f32 / 2 x f64); big ones are
@@ -1771,7 +1775,14 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         Gen &g = *gens[k];
         const int d = ph.domain, ipt = Q.ipt[d];
         appendf(s, "%s{ // phase %zu: domain %d, %d items per tile\n", ind, k, d, ipt);
-        if (ipt <= Q.tpb) appendf(s, "%s  const int i = ngb_tid;\n%s  if (i < %d) {\n", ind, ind, ipt);
+        if (g.has_partner) {
+            // the phase exchanges values between the two threads of an item pair (NGB200_OP_PARTNER = warp shuffle): EVERY
+            // lane executes the body; lanes without an item compute on the tile's first item and store nothing
+            appendf(s, "%s  if (tile * %dLL < p.n[%d]) for (int ngb_i0 = 0; ngb_i0 < %d; ngb_i0 += NGB_TPB) {\n", ind, ipt, d, ipt);
+            appendf(s, "%s    const bool ngb_on = ngb_i0 + ngb_tid < %d && tile * %dLL + ngb_i0 + ngb_tid < p.n[%d];\n", ind, ipt, ipt, d);
+            appendf(s, "%s    const int i = ngb_on ? ngb_i0 + ngb_tid : 0;\n", ind);
+            appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    {\n", ind, ipt, ind);
+        } else if (ipt <= Q.tpb) appendf(s, "%s  const int i = ngb_tid;\n%s  if (i < %d) {\n", ind, ind, ipt);
         else {
             // several items per thread: copy phases (no arithmetic: tile load / store) are unrolled so that the global
             // loads of ALL of a thread's items are in flight together -- one DRAM round trip per phase instead of one per
@@ -1782,7 +1793,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             if ((mode == 1 && arith == 0 && ipt <= 4 * Q.tpb) || mode >= 2) appendf(s, "%s  #pragma unroll\n", ind);
             appendf(s, "%s  for (int i = ngb_tid; i < %d; i += NGB_TPB) {\n", ind, ipt);
         }
-        appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    if (gi < p.n[%d]) {\n", ind, ipt, ind, d);
+        if (!g.has_partner) appendf(s, "%s    const long long gi = tile * %dLL + i;\n%s    if (gi < p.n[%d]) {\n", ind, ipt, ind, d);
         appendf(s, "%s      T x[%d]; T y[%d];\n", ind, g.NX > 0 ? g.NX : 1, g.NY > 0 ? g.NY : 1);
         // row of an indexed access: global arrays use the index value itself, shared buffers the tile-local part
         std::map<std::pair<int, int>, std::string> rows;
@@ -1863,6 +1874,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
         }
         if (g.n_remat > 0) appendf(s, "%s      ngb_body_%zu(x, xp, u%zu, y);\n", ind, k, k);
         else appendf(s, "%s      ngb_body_%zu(x, u%zu, y);\n", ind, k, k);
+        if (g.has_partner) appendf(s, "%s      if (ngb_on) {\n", ind);
         for (size_t j = 0; j < ph.out.size(); ++j) {
             if (Q.records && ph.out[j].kind == NGB200_BIND_SHARED) {
                 const int w = ph.prog->out_width[j];
@@ -1885,6 +1897,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                 else appendf(s, "%s      NGB_ST(%s, y[%d]);\n", ind, a.c_str(), g.yoff[j] + c);
             }
         }
+        if (g.has_partner) appendf(s, "%s      }\n", ind);
         appendf(s, "%s    }\n%s  }\n%s}\n", ind, ind, ind);
         // A barrier separates this phase from the next one in program order -- unless both run over the same domain and
         // touch shared buffers only at their own item (no index): then thread i of the next phase reads exactly what

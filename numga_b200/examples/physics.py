@@ -313,6 +313,23 @@ def _block_structure(n_bodies, index_sets, max_block=1024):
     raise ValueError('constraints do not decompose into independent blocks of <= %d consecutive bodies; use FusedStep' % max_block)
 
 
+def _partner(x):
+    """`x` as computed by the thread of the OTHER side of the same constraint (items 2k and 2k + 1 are the two sides:
+    adjacent lanes, one warp shuffle per component)."""
+    from numga_b200.trace import SymArray
+    v = x.values
+    return x.context.multivector(values=SymArray(v.trace, [v.trace.partner(r) for r in v.regs]), subspace=x.subspace)
+
+
+def _ordered(side, mine, theirs):
+    """(value of side 0, value of side 1) given this thread's and its partner's value; `side` > 0 on side 0."""
+    from numga_b200.trace import SymArray
+    t, s = mine.values.trace, side.values.regs[0]
+    pick = lambda a, b: mine.context.multivector(
+        values=SymArray(t, [t.select_gt0(s, ra, rb) for ra, rb in zip(a.values.regs, b.values.regs)]), subspace=mine.subspace)
+    return pick(mine, theirs), pick(theirs, mine)
+
+
 class ChainStep:
     """The sub-step as ONE chain-resident kernel (numga_b200/pipeline.py): a CTA owns a tile of whole chains, loads
     motor / rate / inverse inertia into shared memory once, runs  pre -> apply per colour set -> post -> v_apply per
@@ -325,7 +342,7 @@ class ChainStep:
     formulas are the same traced python bodies `FusedStep` uses.  `integrate(bodies, dt)` = `unroll` sub-steps of dt."""
 
     def __init__(self, bodies, constraint_sets, unroll=1, bodies_per_tile=None, threads_per_tile=0, exploit_zeros=False,
-                 recompute_maps=None):
+                 recompute_maps=None, pairs=False):
         from numga_b200.pipeline import Pipeline, compact_operator, expand_operator
         from numga_b200.backend import _OperatorKey, kernel_space
         import torch
@@ -337,6 +354,14 @@ class ChainStep:
             bodies_per_tile = 384 if ctx.dtype == torch.float32 else 192      # measured on B200 (profiles/r02_chain_sweep.txt)
         k = max(1, bodies_per_tile // block)                       # whole blocks (chains) per tile
         self.block, self.blocks_per_tile = block, k
+        # `pairs`: TWO threads per constraint in the constraint phases, one per side -- the reference's own formulation (its
+        # constraint arrays are [2, c]: numga/examples/physics/core.py:104-167) with the two values that couple the sides
+        # (the other anchor / velocity line, the other side's inertial compliance) exchanged by warp shuffle
+        # (NGB200_OP_PARTNER).  Half the registers per thread, twice the threads: one body per thread in the body phases.
+        self.pairs = bool(pairs)
+        if self.pairs:
+            assert not exploit_zeros, 'pairs=True re-evaluates the anchor maps (no tables to inspect)'
+            per_block = [2 * c for c in per_block]
         if not threads_per_tile:
             # one thread per constraint in the constraint phases (every warp busy there: they are 60 % of the work), two
             # bodies per thread in the body phases: 8.07 vs 6.60 G body-steps/s against one thread per body
@@ -413,8 +438,50 @@ class ChainStep:
         def v_apply_from_anchors(m0, m1, r0, r1, inv0, inv1, a0, a1, compliance, dt):
             return v_apply(m0, m1, r0, r1, inv0, inv1, a0.inertia_map(), a1.inertia_map(), compliance, dt)
 
+        def share(side, mine):
+            return _ordered(side, mine, _partner(mine))
+
+        def apply_side(m, inv, a, compliance, side, dt):
+            """One side of `Constraint.apply` (core.py:104-120): this thread's body, anchor and inverse inertia."""
+            inv = unpack(inv)
+            w0, w1 = share(side, m >> a)
+            forque = w0 & w1
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            d = m << direction
+            s = inv(d)
+            c0, c1 = share(side, s & d)
+            multiplier = magnitude / (compliance / (dt * dt) + (c0 + c1))
+            return motor_add_step(m, s * (side * 0.5) * multiplier)
+
+        def v_apply_side(m, r, inv, a, compliance, side, dt):
+            """One side of `Constraint.v_apply` (core.py:129-146)."""
+            inv = unpack(inv)
+            v0, v1 = share(side, m >> a.inertia_map()(r))
+            forque = -(v0 * 0.5 + v1 * -0.5)
+            magnitude = forque.norm()
+            direction = forque / (magnitude + 1e-26)
+            d = m << direction
+            s = inv(d)
+            c0, c1 = share(side, s & d)
+            multiplier = magnitude / (compliance * 0 + (c0 + c1))
+            return r + s * (side * 0.5) * multiplier
+
+        if self.pairs:
+            sides = []
+            for j, c in enumerate(self.sets):
+                idx = pipe.index(f'set{j}/idx', f'set{j}')
+                a = pipe.array(f'set{j}/a', c.anchors.subspace, f'set{j}')
+                comp = pipe.array(f'set{j}/compliance', c.compliance.subspace, f'set{j}')
+                side = pipe.array(f'set{j}/side', S.scalar(), f'set{j}')
+                sides.append((idx, a, comp, side))
+            for j, (idx, a, comp, side) in enumerate(sides):
+                pipe.phase(f'set{j}', apply_side, [s_motor[idx], s_inv[idx], a, comp, side, dt], [s_motor[idx]])
+            pipe.phase('body', post, [s_motor, s_old, dt], [s_motor, s_rate])
+            for j, (idx, a, comp, side) in enumerate(sides):
+                pipe.phase(f'set{j}', v_apply_side, [s_motor[idx], s_rate[idx], s_inv[idx], a, comp, side, dt], [s_rate[idx]])
         per_set = []
-        for j, c in enumerate(self.sets):
+        for j, c in enumerate(self.sets if not self.pairs else []):
             i0, i1 = pipe.index(f'set{j}/i0', f'set{j}'), pipe.index(f'set{j}/i1', f'set{j}')
             a0, a1 = pipe.array(f'set{j}/a0', c.anchors.subspace, f'set{j}'), pipe.array(f'set{j}/a1', c.anchors.subspace, f'set{j}')
             map_space = _OperatorKey(c.anchors_map.axes, map_masks[j])
@@ -423,7 +490,8 @@ class ChainStep:
             per_set.append((i0, i1, a0, a1, m0, m1, comp))
         for j, (i0, i1, a0, a1, m0, m1, comp) in enumerate(per_set):
             pipe.phase(f'set{j}', apply, [s_motor[i0], s_motor[i1], s_inv[i0], s_inv[i1], a0, a1, comp, dt], [s_motor[i0], s_motor[i1]])
-        pipe.phase('body', post, [s_motor, s_old, dt], [s_motor, s_rate])
+        if not self.pairs:
+            pipe.phase('body', post, [s_motor, s_old, dt], [s_motor, s_rate])
         for j, (i0, i1, a0, a1, m0, m1, comp) in enumerate(per_set):
             if self.recompute_maps:
                 pipe.phase(f'set{j}', v_apply_from_anchors,
@@ -442,6 +510,22 @@ class ChainStep:
             raise
         # per-set operands never change between steps: resolved once
         self._static = {}
+        if self.pairs:
+            # the reference's [2, c] arrays re-laid out side-major inside each constraint: item 2k + s = side s of constraint k
+            from numga_b200.backend import to_soa
+            for j, c in enumerate(self.sets):
+                nc = int(c.body_idx.shape[1])
+                interleave = lambda v: to_soa(v.movedim(0, 1).reshape((2 * nc,) + tuple(v.shape[2:])))
+                side = torch.tensor([1.0, -1.0], dtype=ctx.dtype, device=ctx.device).repeat(nc)[:, None]
+                self._static.update({
+                    f'set{j}/idx': c.body_idx.movedim(0, 1).reshape(-1).contiguous(),
+                    f'set{j}/a': ctx.multivector(values=interleave(c.anchors.values), subspace=c.anchors.subspace),
+                    f'set{j}/compliance': ctx.multivector(values=to_soa(c.compliance.values.repeat_interleave(2, dim=0)),
+                                                          subspace=c.compliance.subspace),
+                    f'set{j}/side': ctx.multivector(values=to_soa(side), subspace=S.scalar())})
+            self._items = {f'set{j}': 2 * int(c.body_idx.shape[1]) for j, c in enumerate(self.sets)}
+            self._items['body'] = n_bodies
+            return
         for j, c in enumerate(self.sets):
             self._static.update({f'set{j}/i0': c.body_idx[0].contiguous(), f'set{j}/i1': c.body_idx[1].contiguous(),
                                  f'set{j}/a0': c.anchors[0], f'set{j}/a1': c.anchors[1],

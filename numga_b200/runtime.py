@@ -16,10 +16,10 @@ FAST, FAITHFUL = 0, 1
 VARYING, BROADCAST, INDEXED, REDUCED, TILED = 0, 1, 2, 3, 4
 
 (OP_INPUT, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SQRT, OP_RSQRT, OP_RCP, OP_ABS,
- OP_NAN_TO_NUM, OP_FMA, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_SELECT_GT0, OP_ATAN2) = range(22)
+ OP_NAN_TO_NUM, OP_FMA, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_MIN, OP_MAX, OP_SELECT_GT0, OP_ATAN2, OP_PARTNER) = range(23)
 
 N_OPERANDS = {OP_INPUT: 0, OP_CONST: 0, OP_PARAM: 0, OP_NEG: 1, OP_SQRT: 1, OP_RSQRT: 1, OP_RCP: 1, OP_ABS: 1,
-              OP_EXP: 1, OP_LOG: 1, OP_SIN: 1, OP_COS: 1, OP_FMA: 3, OP_SELECT_GT0: 3}
+              OP_EXP: 1, OP_LOG: 1, OP_SIN: 1, OP_COS: 1, OP_FMA: 3, OP_SELECT_GT0: 3, OP_PARTNER: 1}
 
 
 class NGB200Error(RuntimeError):

@@ -205,6 +205,10 @@ class Trace:
         f = self._fold(np.arctan2, y, x)
         return f if f is not None else self._emit(rt.OP_ATAN2, y, x)
 
+    def partner(self, a):
+        """The value `a` as computed by the thread of the paired item (i ^ 1): pipeline phases only (NGB200_OP_PARTNER)."""
+        return a if self.uniform[a] else self._emit(rt.OP_PARTNER, a)
+
     def select_gt0(self, cond, a, b):
         """cond > 0 ? a : b"""
         if a == b:

@@ -14,7 +14,8 @@ bpt = int(sys.argv[4]) if len(sys.argv) > 4 else None
 tpt = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 ctx = B200Context('x+y+z+w0', dtype=torch.float32 if tag == 'f32' else torch.float64)
 big, bsets = physics_state(ctx, (1 << logn) // 12, 0)
-cs = ChainStep(big, bsets, unroll=unroll, bodies_per_tile=bpt, threads_per_tile=tpt)
+pairs = os.environ.get('CHAIN_PAIRS', '0') == '1'          # two threads per constraint (ChainStep(pairs=True))
+cs = ChainStep(big, bsets, unroll=unroll, bodies_per_tile=bpt, threads_per_tile=tpt, pairs=pairs)
 state = [big]
 
 
@@ -23,4 +24,4 @@ def step():
 ms = time_steps(step, 5, 2)
 n = big.motor.shape[0]
 knobs = {k: v for k, v in os.environ.items() if k.startswith('NGB200') and 'CACHE' not in k}
-print(f'chain {tag} 2^{logn} unroll {unroll} bpt {bpt} tpt {tpt} {knobs}: {ms:.3f} ms, {n * unroll / ms / 1e6:.3f} G body-steps/s, info {cs.compiled.program.info}', flush=True)
+print(f'chain {tag} 2^{logn} unroll {unroll} bpt {bpt} tpt {tpt} pairs {int(pairs)} {knobs}: {ms:.3f} ms, {n * unroll / ms / 1e6:.3f} G body-steps/s, info {cs.compiled.program.info}', flush=True)

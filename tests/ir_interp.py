@@ -44,6 +44,7 @@ def run_ir(ir, inputs, dtype, params=()):
             elif op == rt.OP_MAX: v = np.maximum(vals[a], vals[b])
             elif op == rt.OP_SELECT_GT0: v = np.where(vals[a] > 0, vals[b], vals[c])
             elif op == rt.OP_ATAN2: v = np.arctan2(vals[a], vals[b])
+            elif op == rt.OP_PARTNER: v = vals[a].reshape(-1, 2)[:, ::-1].reshape(-1)      # items come in pairs (2k, 2k + 1)
             else: raise ValueError(op)
             vals.append(np.asarray(v, dtype=dtype))
     outs = [np.zeros((batch, w), dtype=dtype) for w in ir['out_width']]

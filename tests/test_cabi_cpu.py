@@ -146,7 +146,7 @@ int main(void) {
            offsetof(ngb200_program_desc, stores), offsetof(ngb200_program_desc, vec));
     printf("%zu %zu\\n", sizeof(ngb200_program_info), offsetof(ngb200_program_info, cubin_bytes));
     printf("%d %d %d %d %d\\n", NGB200_VARYING, NGB200_BROADCAST, NGB200_INDEXED, NGB200_REDUCED, NGB200_TILED);
-    printf("%d %d %d %d %d\\n", NGB200_OP_INPUT, NGB200_OP_FMA, NGB200_OP_SELECT_GT0, NGB200_OP_ATAN2, NGB200_OP_COUNT_);
+    printf("%d %d %d %d %d %d\\n", NGB200_OP_INPUT, NGB200_OP_FMA, NGB200_OP_SELECT_GT0, NGB200_OP_ATAN2, NGB200_OP_PARTNER, NGB200_OP_COUNT_);
     return 0;
 }
 ''')
@@ -160,14 +160,14 @@ int main(void) {
     assert lines[1].split() == [str(x) for x in (ctypes.sizeof(d), d.consts.offset, d.stores.offset, d.vec.offset)]
     assert lines[2].split() == [str(ctypes.sizeof(rt.ProgramInfo)), str(rt.ProgramInfo.cubin_bytes.offset)]
     assert lines[3].split() == [str(x) for x in (rt.VARYING, rt.BROADCAST, rt.INDEXED, rt.REDUCED, rt.TILED)]
-    assert lines[4].split() == [str(x) for x in (rt.OP_INPUT, rt.OP_FMA, rt.OP_SELECT_GT0, rt.OP_ATAN2, rt.OP_ATAN2 + 1)]
+    assert lines[4].split() == [str(x) for x in (rt.OP_INPUT, rt.OP_FMA, rt.OP_SELECT_GT0, rt.OP_ATAN2, rt.OP_PARTNER, rt.OP_PARTNER + 1)]
 
 
 def test_every_opcode_generates_code_in_both_precisions():
     """One program per arithmetic opcode of include/numga_b200.h (compile only, no GPU): the generator knows them all,
     in the scalar and in the packed (two items per thread) emitters."""
-    ops = [getattr(rt, n) for n in dir(rt) if n.startswith('OP_') and n not in ('OP_INPUT', 'OP_CONST', 'OP_PARAM')]
-    assert len(ops) == rt.OP_ATAN2 + 1 - 3
+    ops = [getattr(rt, n) for n in dir(rt) if n.startswith('OP_') and n not in ('OP_INPUT', 'OP_CONST', 'OP_PARAM', 'OP_PARTNER')]
+    assert len(ops) == rt.OP_PARTNER - 3           # (OP_PARTNER exists in pipeline phases only: tested there)
     for dtype in (rt.F32, rt.F64):
         for op in ops:
             n = rt.N_OPERANDS.get(op, 2)

@@ -153,6 +153,49 @@ def test_physics_generic_and_fused_step_cpu_emulated():
             _block_structure(12, [torch.tensor([[0, 5], [11, 6]])], max_block=6)
 
 
+def _pairs_against_default(ctx, tag, n_chains=5, bodies_per_tile=24):
+    """ChainStep(pairs=True) -- two threads per constraint, one per side, coupling values exchanged by warp shuffle --
+    against the one-thread-per-constraint ChainStep on perturbed replicated chains (a partial last tile included)."""
+    from numga_b200.examples.physics import ChainStep, replicate_chains, setup_bodies
+    bodies, sets = setup_bodies(ctx, n_bodies=12)
+    big, bsets = replicate_chains(bodies, sets, n_chains)
+    rng = np.random.default_rng(7)
+    big = big.copy(rate=big.rate + ctx.multivector.bivector(0.3 * rng.standard_normal((12 * n_chains, 6))))
+    ref = ChainStep(big, bsets, unroll=3, bodies_per_tile=bodies_per_tile).integrate(big, DT)
+    cp = ChainStep(big, bsets, unroll=3, bodies_per_tile=bodies_per_tile, pairs=True)
+    got = cp.integrate(big, DT)
+    return cp, _np(ref.motor), _np(ref.rate), _np(got.motor), _np(got.rate)
+
+
+def _np(mv):
+    return mv.values.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('mode', ['fast', 'faithful'])
+def test_chain_step_with_two_threads_per_constraint_cpu_emulated(mode):
+    from cpu_emulation import emulate_launches, emulated_context
+    with emulate_launches():
+        ctx = emulated_context('x+y+z+w0', torch.float64, mode=mode)
+        cp, m0, r0, m1, r1 = _pairs_against_default(ctx, 'f64')
+        assert cp.compiled.pipe.items_per_tile[1:] == [2 * 6 * 2, 2 * 5 * 2] and cp.compiled.pipe.threads_per_tile == 32
+        assert np.array_equal(m0, m1) and np.array_equal(r0, r1)          # same operations in the same order, per side
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+@pytest.mark.parametrize('mode', ['fast', 'faithful'])
+def test_chain_step_with_two_threads_per_constraint_gpu(tag, mode):
+    from numga_b200 import B200Context
+    ctx = B200Context('x+y+z+w0', dtype=torch.float32 if tag == 'f32' else torch.float64, mode=mode)
+    for n_chains, bpt in ((5, 24), (70, None)):
+        cp, m0, r0, m1, r1 = _pairs_against_default(ctx, tag, n_chains, bpt)
+        if mode == 'faithful':
+            assert np.array_equal(m0, m1) and np.array_equal(r0, r1)
+        else:                                    # FMA contraction is chosen per program: equal to rounding
+            mt, rt_ = physics_gate(tag, 3)
+            assert _err(m1, m0) < mt and _err(r1, r0) < rt_
+
+
 # ---- GPU tier ----------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('tag', ['f64', 'f32'])
