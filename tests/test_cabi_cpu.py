@@ -210,3 +210,18 @@ def test_pipeline_c_abi_compiles_and_validates():
         rt.PipelineProgram(rt.F32, rt.FAST, [64, 63], globals_, [(1, 0)], phases, (1, 3), 0)
     with pytest.raises(rt.NGB200Error, match='shared memory'):
         rt.PipelineProgram(rt.F32, rt.FAST, [1024, 63], globals_, [(60, 0)], phases, (0, 0), 0)
+
+
+def test_partner_opcode_is_a_warp_convergent_pipeline_feature():
+    """NGB200_OP_PARTNER (value of the paired item i ^ 1, one warp shuffle): accepted in pipeline phases, where the phase
+    loop is emitted so that EVERY lane executes the body (lanes without an item compute on the tile's first item and
+    store nothing); refused in ordinary programs, whose kernels map several items to a thread."""
+    I = rt.BIND_GLOBAL
+    swap = dict(in_width=[1], out_width=[1], n_params=0, consts=[], stores=[(0, 0, 2)],
+                instr=[(rt.OP_INPUT, 0, 0, 0), (rt.OP_PARTNER, 0, 0, 0), (rt.OP_SUB, 0, 1, 0)])
+    p = rt.PipelineProgram(rt.F64, rt.FAITHFUL, [70], [(1, 0, False), (1, 0, False)], [], [(swap, 0, [(I, 0, -1)], [(I, 1, -1)])], (0, 0), 0)
+    src = p.source
+    assert '__shfl_xor_sync(0xffffffffu' in src and 'ngb_on' in src and 'if (ngb_on) {' in src
+    assert 'for (int ngb_i0 = 0; ngb_i0 < 70; ngb_i0 += NGB_TPB)' in src          # uniform trip count for all lanes
+    with pytest.raises(rt.NGB200Error, match='pipeline phases'):
+        rt.Program.from_ir(rt.F32, rt.FAST, [1], [rt.VARYING], [1], [rt.VARYING], 0, [], swap['instr'], swap['stores'])
