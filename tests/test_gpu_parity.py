@@ -297,6 +297,46 @@ def _device_mv(ctx, sub, n, seed, scale=1.0):
     return ctx.multivector(values=v, subspace=sub)
 
 
+@pytest.mark.parametrize('config', ['1', '2', '2-faithful', '3-f32', '3-f64', '4'])
+def test_parity_against_the_oracle_on_2p20_items_per_config(config):
+    """"Parity batch: 2^20 items per config" -- the timed kernels of BASELINE configs 1-4 against the oracle
+    port of the numpy backend on the SAME seeded inputs, max over items of |gpu - oracle|_inf / |oracle|_inf within
+    1e-5 (fp32) / 1e-12 (fp64); the exp -> normalized -> log chain within the measured chain gate
+    (tests/tolerances.py, profiles/r02_tolerances.md).  (config 3 in fp64: 2^18 items, the op-by-op numpy chain is slow.)"""
+    rng = np.random.default_rng(2020)
+    n = 1 << 20
+    if config in ('1', '2', '2-faithful'):
+        mode = 'faithful' if config.endswith('faithful') else 'fast'
+        ctx, oc = _ctx((3, 0, 1), np.float32, mode), O.context((3, 0, 1), np.float32)
+        if config == '1':
+            a, b = rng.standard_normal((n, 8)).astype(np.float32), rng.standard_normal((n, 8)).astype(np.float32)
+            got = (ctx.multivector.motor(a) * ctx.multivector.motor(b)).numpy()
+            want = (oc.multivector('even_grade', a) * oc.multivector('even_grade', b)).values
+        else:
+            R, p = rng.standard_normal(8).astype(np.float32), rng.standard_normal((n, 4)).astype(np.float32)
+            got = (ctx.multivector.motor(R) >> ctx.multivector.antivector(p)).numpy()
+            want = (oc.multivector('even_grade', R) >> oc.multivector('antivector', p)).values
+        assert got.shape == want.shape == (n, want.shape[-1])
+        assert _rel_err(got, want) <= TOL[np.float32]
+    elif config.startswith('3'):
+        dtype = np.float32 if config.endswith('f32') else np.float64
+        m = n if dtype == np.float32 else n >> 2
+        hb = (0.5 * rng.standard_normal((m, 6))).astype(dtype)
+        ctx, oc = _ctx((3, 0, 1), dtype), O.context((3, 0, 1), dtype)
+        got = ctx.jit(lambda x: x.exp().normalized().motor_log())(ctx.multivector.bivector(hb)).numpy()
+        with np.errstate(all='ignore'):
+            want = oc.multivector('bivector', hb).exp().normalized().motor_log().values
+        assert _rel_err(got, want) <= CHAIN_TOL[dtype]
+        assert _rel_err(got, hb) <= (2e-3 if dtype == np.float32 else 1e-9)          # and the round trip returns its input
+    else:
+        ctx, oc = _ctx((4, 1, 0), np.float32), O.context((4, 1, 0), np.float32)
+        x, y = rng.standard_normal((n, 32)).astype(np.float32), rng.standard_normal((n, 32)).astype(np.float32)
+        F = ctx.subspace.full()
+        got = (ctx.multivector(values=x, subspace=F) * ctx.multivector(values=y, subspace=F)).numpy()
+        want = (oc.multivector('multivector', x) * oc.multivector('multivector', y)).values
+        assert _rel_err(got, want) <= TOL[np.float32]
+
+
 def test_config2_sandwich_256M_points_round_trip():
     """R >> p followed by ~R >> . returns p for a normalized motor, at the full 2^28 points."""
     ctx = _ctx((3, 0, 1), np.float32)
