@@ -68,20 +68,9 @@ class B200MultiVector(AbstractMultiVector):
     def at(self):
         """`mv.at[idx].set(rows)` (numga/multivector/helper.py): with a lazy engine the kernel that computes `rows` writes
         them straight into the copy; otherwise numga's generic helper (`context.set_array`)."""
-        ctx = self.context
-        if not ctx.engine.lazy:
+        if not self.context.engine.lazy:
             return AbstractMultiVector.at.fget(self)
-        this = self
-
-        class _At:
-            def __getitem__(self, idx):
-                class _Set:
-                    def set(self, rows):
-                        if isinstance(rows, B200MultiVector):
-                            rows = ctx.to_engine(rows)
-                        return ctx.from_engine(ctx.to_engine(this).at[idx].set(rows))
-                return _Set()
-        return _At()
+        return _LazyAt(self)
 
     def __len__(self):
         return self.shape[0]
@@ -115,6 +104,23 @@ class B200MultiVector(AbstractMultiVector):
 
     def numpy(self):
         return self.values.detach().cpu().numpy()
+
+
+class _LazyAt:
+    """`mv.at[idx].set(rows)` forwarded to the engine multivector (row scatter inside the kernel that computes `rows`)."""
+    __slots__ = ('mv', 'idx')
+
+    def __init__(self, mv, idx=None):
+        self.mv, self.idx = mv, idx
+
+    def __getitem__(self, idx):
+        return _LazyAt(self.mv, idx)
+
+    def set(self, rows):
+        ctx = self.mv.context
+        if isinstance(rows, B200MultiVector):
+            rows = ctx.to_engine(rows)
+        return ctx.from_engine(ctx.to_engine(self.mv).at[self.idx].set(rows))
 
 
 def _engine_method(name):
