@@ -1648,7 +1648,8 @@ struct ngb200_pipeline {
     bool records = true;
     std::vector<size_t> rec_off;              // element offset of every shared buffer inside its domain's record
     std::vector<size_t> dom_base;             // element offset of every domain's record array
-    std::vector<int> dom_chunks;              // 16-byte chunks per record, per domain
+    std::vector<int> dom_chunks;              // chunks per record, per domain
+    int vw = 4, pad_shift = 3;                // elements per chunk (fp32: 4 = 16 bytes; fp64: 1 = 8 bytes), one padding chunk per 2^pad_shift rows
     std::string source, hash;
     std::vector<char> cubin;
     bool cache_hit = false;
@@ -1828,7 +1829,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             const ngb200_instr &I = ph.prog->instr[v];
             if (I.op == NGB200_OP_INPUT && g.live[v] && !g.uniform[v]) used[g.xoff[I.a] + I.b] = 1;
         }
-        const int VW = f64 ? 2 : 4;                         // elements per 16-byte chunk
+        const int VW = Q.records ? Q.vw : (f64 ? 2 : 4);    // elements per chunk of the record layout
         const char *VTn = f64 ? "double2" : "float4";
         static const char *lane4[4] = {"x", "y", "z", "w"};
         // element offset of (row r) of shared buffer `slot` in the record layout
@@ -1836,8 +1837,8 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
             const int dd = Q.sdomain[b.slot];
             std::string r = b.index >= 0 ? row_of(b) : std::string("i");
             char buf[256];
-            snprintf(buf, sizeof buf, "sm + %zu + (%s * %d + (%s >> 3)) * %d + %zu", Q.dom_base[dd], r.c_str(), Q.dom_chunks[dd],
-                     r.c_str(), VW, Q.rec_off[b.slot]);
+            snprintf(buf, sizeof buf, "sm + %zu + (%s * %d + (%s >> %d)) * %d + %zu", Q.dom_base[dd], r.c_str(), Q.dom_chunks[dd],
+                     r.c_str(), Q.pad_shift, VW, Q.rec_off[b.slot]);
             return buf;
         };
         if (g.n_remat > 0) {
@@ -1856,6 +1857,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                     bool any = false;
                     for (int c = c0; c < std::min(w, c0 + VW); ++c) any = any || used[g.xoff[j] + c];
                     if (!any) continue;
+                    if (VW == 1) { appendf(s, "%s        x[%d] = rp[%d];\n", ind, g.xoff[j] + c0, c0); continue; }
                     appendf(s, "%s        { const %s t = *reinterpret_cast<const %s*>(rp + %d);", ind, VTn, VTn, c0);
                     for (int c = c0; c < std::min(w, c0 + VW); ++c)
                         if (used[g.xoff[j] + c]) appendf(s, " x[%d] = t.%s;", g.xoff[j] + c, lane4[c - c0]);
@@ -1881,6 +1883,7 @@ static std::string pipeline_source(ngb200_pipeline &Q, bool ir_order, std::strin
                 std::string base = record_base(ph.out[j]);
                 appendf(s, "%s      { T* rp = %s;\n", ind, base.c_str());
                 for (int c0 = 0; c0 < w; c0 += VW) {           // (the padding lanes of the last chunk belong to this buffer)
+                    if (VW == 1) { appendf(s, "%s        rp[%d] = y[%d];\n", ind, c0, g.yoff[j] + c0); continue; }
                     appendf(s, "%s        { %s t;", ind, VTn);
                     for (int l = 0; l < VW; ++l) {
                         if (c0 + l < w) appendf(s, " t.%s = y[%d];", lane4[l], g.yoff[j] + c0 + l);
@@ -2012,7 +2015,16 @@ extern "C" int ngb200_pipeline_create(const ngb200_pipeline_desc *d, ngb200_pipe
     Q->smem = off * es;
     Q->records = env_int("NGB200_PIPE_RECORDS", 1) != 0;
     if (Q->records) {
-        const int VW = 16 / es;
+        // fp32: 16-byte chunks (float4 accesses, a quarter warp per wavefront), records of an ODD number of chunks + one chunk
+        // every 8 rows.  fp64: most accesses are the 8-byte re-reads of wide tables at their point of use (a HALF warp per
+        // wavefront): with 16-byte chunks the row stride is an even number of 8-byte units and rows 8-15 fall on the banks of
+        // rows 0-7 (ncu: 647 M conflicts in 1 276 M load wavefronts); 8-byte chunks, an odd number per record and one
+        // padding unit every 16 rows make unit-stride and stride-2 rows conflict-free for 8-byte accesses
+        // (NGB200_PIPE_F64_UNITS=0 restores the 16-byte chunks).
+        const bool units = d->dtype == NGB200_F64 && env_int("NGB200_PIPE_F64_UNITS", 1) != 0;
+        Q->vw = units ? 1 : 16 / es;
+        Q->pad_shift = units ? 4 : 3;
+        const int VW = Q->vw;
         Q->rec_off.assign(d->n_shared, 0);
         Q->dom_base.assign(d->n_domains, 0);
         Q->dom_chunks.assign(d->n_domains, 0);
@@ -2022,12 +2034,12 @@ extern "C" int ngb200_pipeline_create(const ngb200_pipeline_desc *d, ngb200_pipe
             for (int k = 0; k < d->n_shared; ++k)
                 if (Q->sdomain[k] == dd) { Q->rec_off[k] = rec; rec += (size_t)(Q->swidth[k] + VW - 1) / VW * VW; }
             int chunks = (int)(rec / VW);
-            if (chunks && chunks % 2 == 0) chunks += 1;                      // odd number of 16-byte chunks per record
+            if (chunks && chunks % 2 == 0) chunks += 1;                      // odd number of chunks per record
             Q->dom_chunks[dd] = chunks;
             Q->dom_base[dd] = total;
-            if (chunks) total += ((size_t)Q->ipt[dd] * chunks + (Q->ipt[dd] >> 3) + 1) * VW;
+            if (chunks) total += ((size_t)Q->ipt[dd] * chunks + (Q->ipt[dd] >> Q->pad_shift) + 1) * VW;
         }
-        Q->smem = total * es;
+        Q->smem = (total * es + 15) / 16 * 16;
     }
     if (Q->smem > 227 * 1024) return fail(NGB200_ERR_INVALID, "tile needs %zu bytes of shared memory (limit 232448)", Q->smem);
     Q->tpb = d->threads_per_tile > 0 ? d->threads_per_tile : std::min(256, (max_ipt + 31) / 32 * 32);
